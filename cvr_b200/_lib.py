@@ -1,0 +1,95 @@
+"""ctypes binding of the C ABI in include/cvr_b200.h (libcvr_b200.so, built in-tree).
+
+There is deliberately no fallback: if the CUDA library is missing, loading fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libcvr_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class CvrCsr(C.Structure):  # cvr_csr_t
+    _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int64), ("nnz", C.c_int64),
+                ("val", C.c_void_p), ("col", C.c_void_p),
+                ("row_delim32", C.c_void_p), ("row_delim64", C.c_void_p)]
+
+
+class CvrArrays(C.Structure):  # cvr_arrays_t
+    _fields_ = [("vals", C.c_void_p), ("cols", C.c_void_p), ("record", C.c_void_p),
+                ("nnz_rows", C.c_void_p), ("final_2", C.c_void_p), ("split", C.c_void_p)]
+
+
+class CvrInfo(C.Structure):  # cvr_info_t
+    _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int64), ("nnz", C.c_int64),
+                ("n_chunks", C.c_int32), ("device", C.c_int32),
+                ("n_records", C.c_int64), ("record_ints", C.c_int64),
+                ("algorithmic_bytes", C.c_int64),
+                ("convert_seconds", C.c_double), ("create_seconds", C.c_double),
+                ("kernel_launches", C.c_int64), ("device_bytes", C.c_int64)]
+
+
+class CvrHostCsr(C.Structure):  # cvr_host_csr_t
+    _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int64), ("nnz", C.c_int64),
+                ("nnz_file", C.c_int64), ("val", c_double_p), ("col", c_int32_p),
+                ("row_delim32", c_int32_p), ("row_delim64", c_int64_p)]
+
+
+MM_REF_LAST_DELIM = 1
+MM_KEEP_LAST_LINE = 2
+
+# every symbol include/cvr_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "cvr_abi_version": (C.c_int, []),
+    "cvr_last_error": (C.c_char_p, []),
+    "cvr_device_init": (C.c_int, [C.c_int]),
+    "cvr_read_matrix_market": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(CvrHostCsr)]),
+    "cvr_free_host_csr": (None, [C.POINTER(CvrHostCsr)]),
+    "cvr_record_ints": (C.c_int64, [C.c_int64, C.c_int32]),
+    "cvr_auto_chunks": (C.c_int, [C.c_int64, C.c_int, c_int32_p]),
+    "cvr_create": (C.c_int, [C.POINTER(CvrCsr), C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
+    "cvr_create_from_device": (C.c_int, [C.POINTER(CvrCsr), C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
+    "cvr_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, c_double_p]),
+    "cvr_spmv_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cvr_export": (C.c_int, [C.c_void_p, C.POINTER(CvrArrays)]),
+    "cvr_get_info": (C.c_int, [C.c_void_p, C.POINTER(CvrInfo)]),
+    "cvr_device_vectors": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "cvr_destroy": (None, [C.c_void_p]),
+}
+
+_lib = None
+
+
+class CvrError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libcvr_b200 error {code}: {message}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA library is the only implementation of this path "
+                "(no CPU fallback). Build it with `python -m cvr_b200.build`.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError = ABI drift, fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if lib.cvr_abi_version() != 1:
+            raise RuntimeError("libcvr_b200 ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise CvrError(rc, load().cvr_last_error().decode(errors="replace"))

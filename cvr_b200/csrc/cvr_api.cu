@@ -1,0 +1,416 @@
+// C ABI of libcvr_b200 (include/cvr_b200.h): handle, device memory, timing.
+// The compute lives in cvr_convert.cu and cvr_spmv.cu; there is no host fallback.
+#include "../../include/cvr_b200.h"
+#include "cvr_internal.h"
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+thread_local char g_cvr_err[512] = "";
+
+// shared with cvr_mm_reader.cpp
+int cvr_set_error(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_cvr_err, sizeof(g_cvr_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define fail cvr_set_error
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return fail(CVR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+double wall_seconds()
+{
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+struct cvr_handle {
+    int device = 0;
+    int64_t n_rows = 0, n_cols = 0, nnz = 0;
+    int32_t n_chunks = 0;
+    int64_t record_ints = 0;
+    int64_t n_records = 0;
+    // device arrays (the CVR structure)
+    double* vals = nullptr;
+    int32_t* cols = nullptr;
+    int32_t* record = nullptr;
+    CvrChunk* chunks = nullptr;
+    // device vectors for the host-facing call
+    double* x = nullptr;
+    double* y = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double convert_seconds = 0.0, create_seconds = 0.0;
+    int64_t launches = 0;
+    int64_t device_bytes = 0;
+    std::vector<CvrChunk> host_chunks; // copy of the descriptors (export / info)
+
+    ~cvr_handle()
+    {
+        cudaSetDevice(device);
+        cudaFree(vals);
+        cudaFree(cols);
+        cudaFree(record);
+        cudaFree(chunks);
+        cudaFree(x);
+        cudaFree(y);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+template <typename T>
+cudaError_t dev_alloc(cvr_handle* h, T** p, size_t count)
+{
+    const size_t bytes = sizeof(T) * (count ? count : 1);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+    if (e == cudaSuccess) h->device_bytes += (int64_t)bytes;
+    return e;
+}
+
+int check_csr(const cvr_csr_t* csr, int32_t n_chunks)
+{
+    if (!csr) return fail(CVR_ERR_INVALID, "csr is NULL");
+    if (!csr->val || !csr->col) return fail(CVR_ERR_INVALID, "csr val/col is NULL");
+    if ((csr->row_delim32 == nullptr) == (csr->row_delim64 == nullptr))
+        return fail(CVR_ERR_INVALID, "exactly one of row_delim32 / row_delim64 must be set");
+    if (csr->n_rows < 1 || csr->n_cols < 1)
+        return fail(CVR_ERR_INVALID, "empty matrix (%lld x %lld)", (long long)csr->n_rows,
+                    (long long)csr->n_cols);
+    if (csr->n_rows > 0x7ffffff0LL || csr->n_cols > 0x7ffffff0LL)
+        return fail(CVR_ERR_RANGE, "row/column ids must fit int32");
+    if (csr->nnz < 16 || csr->nnz % 16 != 0)
+        return fail(CVR_ERR_INVALID, "nnz = %lld must be a positive multiple of 16 (spmv.cpp:457)",
+                    (long long)csr->nnz);
+    if (csr->row_delim32 && csr->nnz > 0x7fffffffLL)
+        return fail(CVR_ERR_RANGE, "nnz >= 2^31 needs row_delim64");
+    if (n_chunks < 0 || (int64_t)n_chunks > csr->nnz / 16)
+        return fail(CVR_ERR_INVALID, "n_chunks = %d must be in [0, nnz/16 = %lld]", n_chunks,
+                    (long long)(csr->nnz / 16));
+    return CVR_OK;
+}
+
+// Conversion proper; `csr` holds DEVICE pointers.
+int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
+{
+    const int32_t T = h->n_chunks;
+    CUDA_TRY(dev_alloc(h, &h->vals, (size_t)h->nnz));
+    CUDA_TRY(dev_alloc(h, &h->cols, (size_t)h->nnz));
+    CUDA_TRY(dev_alloc(h, &h->record, (size_t)h->record_ints));
+    CUDA_TRY(dev_alloc(h, &h->chunks, (size_t)T));
+    CUDA_TRY(dev_alloc(h, &h->x, (size_t)h->n_cols + 1));
+    CUDA_TRY(dev_alloc(h, &h->y, (size_t)h->n_rows + 1));
+
+    int2* segments = nullptr;
+    int32_t* seg_count = nullptr;
+    const size_t seg_entries = (size_t)CVR_SEG_STRIDE * T + (size_t)h->n_rows + 64;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&segments), sizeof(int2) * seg_entries));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&seg_count), sizeof(int32_t) * (size_t)T);
+    if (e != cudaSuccess) {
+        cudaFree(segments);
+        return fail(CVR_ERR_CUDA, "cudaMalloc(seg_count): %s", cudaGetErrorString(e));
+    }
+
+    CvrConvertArgs a{};
+    a.csr_val = csr->val;
+    a.csr_col = csr->col;
+    a.rd32 = csr->row_delim32;
+    a.rd64 = csr->row_delim64;
+    a.nnz = h->nnz;
+    a.n_rows = h->n_rows;
+    a.n_chunks = T;
+    a.cvr_vals = h->vals;
+    a.cvr_cols = h->cols;
+    a.record = h->record;
+    a.chunks = h->chunks;
+    a.segments = segments;
+    a.seg_count = seg_count;
+
+    int rc = CVR_OK;
+    float ms = 0.f;
+    do {
+        // every int the scheduler does not write reads back as -1 (a terminator)
+        if ((e = cudaMemsetAsync(h->record, 0xff, sizeof(int32_t) * (size_t)h->record_ints,
+                                 h->stream)) != cudaSuccess) break;
+        if ((e = cudaEventRecord(h->ev0, h->stream)) != cudaSuccess) break;
+        const int launched = cvr_launch_convert(a, h->stream);
+        if (launched < 0) {
+            e = cudaGetLastError();
+            rc = fail(CVR_ERR_CUDA, "conversion kernel launch failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        h->launches += launched;
+        if ((e = cudaEventRecord(h->ev1, h->stream)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
+        if ((e = cudaEventElapsedTime(&ms, h->ev0, h->ev1)) != cudaSuccess) break;
+    } while (0);
+    cudaFree(segments);
+    cudaFree(seg_count);
+    if (rc != CVR_OK) return rc;
+    if (e != cudaSuccess) return fail(CVR_ERR_CUDA, "conversion failed: %s", cudaGetErrorString(e));
+    h->convert_seconds = ms * 1e-3;
+
+    h->host_chunks.resize((size_t)T);
+    CUDA_TRY(cudaMemcpy(h->host_chunks.data(), h->chunks, sizeof(CvrChunk) * (size_t)T,
+                        cudaMemcpyDeviceToHost));
+    h->n_records = 0;
+    for (const CvrChunk& c : h->host_chunks) h->n_records += c.n_rec + CVR_W;
+    return CVR_OK;
+}
+
+int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_on_device,
+                  cvr_handle_t** out)
+{
+    if (!out) return fail(CVR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = check_csr(csr, n_chunks);
+    if (rc != CVR_OK) return rc;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(CVR_ERR_CUDA, "no CUDA device: libcvr_b200 has no CPU fallback");
+    if (device < 0 || device >= n_dev)
+        return fail(CVR_ERR_INVALID, "device %d out of range [0, %d)", device, n_dev);
+    CUDA_TRY(cudaSetDevice(device));
+    if (n_chunks == 0) {
+        rc = cvr_auto_chunks(csr->nnz, device, &n_chunks);
+        if (rc != CVR_OK) return rc;
+    }
+
+    const double t0 = wall_seconds();
+    cvr_handle* h = new (std::nothrow) cvr_handle();
+    if (!h) return fail(CVR_ERR_INVALID, "out of host memory");
+    h->device = device;
+    h->n_rows = csr->n_rows;
+    h->n_cols = csr->n_cols;
+    h->nnz = csr->nnz;
+    h->n_chunks = n_chunks;
+    h->record_ints = cvr_record_ints(csr->n_rows, n_chunks);
+
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->ev0)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+        delete h;
+        return fail(CVR_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+    }
+
+    cvr_csr_t dev = *csr;
+    double* d_val = nullptr;
+    int32_t* d_col = nullptr;
+    void* d_rd = nullptr;
+    if (!csr_on_device) {
+        const size_t rd_bytes = (size_t)(csr->n_rows + 2) * (csr->row_delim64 ? 8 : 4);
+        if ((e = cudaMalloc(reinterpret_cast<void**>(&d_val), sizeof(double) * (size_t)csr->nnz)) == cudaSuccess &&
+            (e = cudaMalloc(reinterpret_cast<void**>(&d_col), sizeof(int32_t) * (size_t)csr->nnz)) == cudaSuccess &&
+            (e = cudaMalloc(&d_rd, rd_bytes)) == cudaSuccess &&
+            (e = cudaMemcpy(d_val, csr->val, sizeof(double) * (size_t)csr->nnz, cudaMemcpyHostToDevice)) == cudaSuccess &&
+            (e = cudaMemcpy(d_col, csr->col, sizeof(int32_t) * (size_t)csr->nnz, cudaMemcpyHostToDevice)) == cudaSuccess)
+            e = cudaMemcpy(d_rd, csr->row_delim64 ? (const void*)csr->row_delim64 : (const void*)csr->row_delim32,
+                           rd_bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d_val);
+            cudaFree(d_col);
+            cudaFree(d_rd);
+            delete h;
+            return fail(CVR_ERR_CUDA, "CSR upload failed: %s", cudaGetErrorString(e));
+        }
+        dev.val = d_val;
+        dev.col = d_col;
+        dev.row_delim32 = csr->row_delim64 ? nullptr : static_cast<const int32_t*>(d_rd);
+        dev.row_delim64 = csr->row_delim64 ? static_cast<const int64_t*>(d_rd) : nullptr;
+    }
+
+    rc = convert_on_device(h, &dev);
+    cudaFree(d_val);
+    cudaFree(d_col);
+    cudaFree(d_rd);
+    if (rc != CVR_OK) {
+        delete h;
+        return rc;
+    }
+    h->create_seconds = wall_seconds() - t0;
+    *out = h;
+    return CVR_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int cvr_abi_version(void) { return CVR_B200_ABI_VERSION; }
+
+const char* cvr_last_error(void) { return g_cvr_err; }
+
+int cvr_device_init(int device)
+{
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(CVR_ERR_CUDA, "no CUDA device: libcvr_b200 has no CPU fallback");
+    if (device < 0 || device >= n_dev)
+        return fail(CVR_ERR_INVALID, "device %d out of range [0, %d)", device, n_dev);
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(nullptr));
+    return CVR_OK;
+}
+
+int64_t cvr_record_ints(int64_t n_rows, int32_t n_chunks)
+{
+    return 2 * (n_rows + 240 + 32 * (int64_t)n_chunks);
+}
+
+int cvr_auto_chunks(int64_t nnz, int device, int32_t* n_chunks)
+{
+    if (!n_chunks || nnz < 16) return fail(CVR_ERR_INVALID, "bad arguments to cvr_auto_chunks");
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
+        return fail(CVR_ERR_CUDA, "cannot query device %d: no CPU fallback", device);
+    // One warp per chunk.  Aim at ~2K elements (24 KB of stream) per chunk so the fixed
+    // per-chunk cost (15 records, 9 atomics) stays small, but never fewer chunks than fill
+    // every SM with 32 warps; round to a whole number of SM-wide waves.
+    int64_t target_nnz = 2048;
+    if (const char* s = getenv("CVR_CHUNK_NNZ")) {
+        const long long v = atoll(s);
+        if (v >= 16) target_nnz = v;
+    }
+    int64_t t = nnz / target_nnz;
+    const int64_t fill = (int64_t)sms * 32;
+    if (t < fill) t = fill;
+    t = (t + sms - 1) / sms * sms;
+    if (t > nnz / 16) t = nnz / 16;
+    if (t > 0x3fffffff) t = 0x3fffffff;
+    if (t < 1) t = 1;
+    *n_chunks = (int32_t)t;
+    return CVR_OK;
+}
+
+int cvr_create(const cvr_csr_t* csr_host, int32_t n_chunks, int device, cvr_handle_t** out)
+{
+    return create_common(csr_host, n_chunks, device, false, out);
+}
+
+int cvr_create_from_device(const cvr_csr_t* csr_dev, int32_t n_chunks, int device,
+                           cvr_handle_t** out)
+{
+    return create_common(csr_dev, n_chunks, device, true, out);
+}
+
+int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* cuda_stream)
+{
+    if (!h || !x_dev || !y_dev) return fail(CVR_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int launched = cvr_launch_spmv(h->chunks, h->n_chunks, h->vals, h->cols, h->record,
+                                         x_dev, y_dev, h->n_rows,
+                                         static_cast<cudaStream_t>(cuda_stream));
+    if (launched < 0)
+        return fail(CVR_ERR_CUDA, "SpMV launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += launched;
+    return CVR_OK;
+}
+
+int cvr_spmv(cvr_handle_t* h, const double* x_host, double* y_host, int32_t iters,
+             double* seconds_per_iter)
+{
+    if (!h || !x_host || !y_host) return fail(CVR_ERR_INVALID, "NULL argument");
+    if (iters < 1) return fail(CVR_ERR_INVALID, "iters = %d must be >= 1", iters);
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->x, x_host, sizeof(double) * (size_t)(h->n_cols + 1),
+                             cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    for (int32_t it = 0; it < iters; it++) {
+        const int rc = cvr_spmv_device(h, h->x, h->y, h->stream);
+        if (rc != CVR_OK) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(y_host, h->y, sizeof(double) * (size_t)(h->n_rows + 1),
+                             cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (seconds_per_iter) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *seconds_per_iter = (double)ms * 1e-3 / iters;
+    }
+    return CVR_OK;
+}
+
+int cvr_export(cvr_handle_t* h, cvr_arrays_t* o)
+{
+    if (!h || !o) return fail(CVR_ERR_INVALID, "NULL argument");
+    if (h->nnz > 0x7fffffffLL && o->nnz_rows)
+        return fail(CVR_ERR_RANGE, "nnz_rows cannot hold offsets >= 2^31");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (o->vals)
+        CUDA_TRY(cudaMemcpy(o->vals, h->vals, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+    if (o->cols)
+        CUDA_TRY(cudaMemcpy(o->cols, h->cols, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+    if (o->record)
+        CUDA_TRY(cudaMemcpy(o->record, h->record, sizeof(int32_t) * (size_t)h->record_ints,
+                            cudaMemcpyDeviceToHost));
+    for (int32_t t = 0; t < h->n_chunks; t++) {
+        const CvrChunk& c = h->host_chunks[(size_t)t];
+        if (o->nnz_rows) {
+            o->nnz_rows[4 * t + 0] = (int32_t)c.start;
+            o->nnz_rows[4 * t + 1] = (int32_t)(c.start + c.len);
+            o->nnz_rows[4 * t + 2] = c.first_row;
+            o->nnz_rows[4 * t + 3] = c.last_row;
+        }
+        if (o->split) {
+            o->split[2 * t + 0] = c.split0;
+            o->split[2 * t + 1] = c.split1;
+        }
+        if (o->final_2)
+            for (int q = 0; q < CVR_W; q++) o->final_2[16 * t + q] = c.tail[q];
+    }
+    return CVR_OK;
+}
+
+int cvr_get_info(cvr_handle_t* h, cvr_info_t* info)
+{
+    if (!h || !info) return fail(CVR_ERR_INVALID, "NULL argument");
+    info->n_rows = h->n_rows;
+    info->n_cols = h->n_cols;
+    info->nnz = h->nnz;
+    info->n_chunks = h->n_chunks;
+    info->device = h->device;
+    info->n_records = h->n_records;
+    info->record_ints = h->record_ints;
+    info->algorithmic_bytes = 12 * h->nnz + 8 * h->n_records + 56 * (int64_t)h->n_chunks +
+                              8 * (h->n_cols + 1) + 8 * (h->n_rows + 1);
+    info->convert_seconds = h->convert_seconds;
+    info->create_seconds = h->create_seconds;
+    info->kernel_launches = h->launches;
+    info->device_bytes = h->device_bytes;
+    return CVR_OK;
+}
+
+int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev)
+{
+    if (!h) return fail(CVR_ERR_INVALID, "NULL handle");
+    if (x_dev) *x_dev = h->x;
+    if (y_dev) *y_dev = h->y;
+    return CVR_OK;
+}
+
+void cvr_destroy(cvr_handle_t* h) { delete h; }
+
+} // extern "C"

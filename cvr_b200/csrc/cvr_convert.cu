@@ -1,0 +1,285 @@
+// CSR -> CVR conversion on the device (sm_100a).
+//
+// Replaces pre_processing (/root/reference/spmv.cpp:565-1014).  The reference walks
+// every 8-element step of a chunk on one OpenMP thread, refilling empty SIMD lanes
+// (feeding, :821-868) or splitting the longest lane (stealing, :869-943) and gathers
+// 8 values + 8 columns per step (:963-977).  Here the same greedy schedule is split
+// into two kernels:
+//
+//   cvr_schedule_kernel  one THREAD per chunk.  Event-driven restatement of the lane
+//                        scheduler: instead of visiting every step it jumps from one
+//                        "a lane ran empty" event to the next (min over the 8 lane
+//                        counters).  Emits the reference's record / split / tail /
+//                        nnz_rows metadata bit-exactly, plus a scratch list of
+//                        (position, source offset) segment starts.  Integer only.
+//   cvr_permute_kernel   one WARP per chunk.  Bandwidth-bound: expands the segment list
+//                        into a source index per CVR element (32 elements = 4 steps x 8
+//                        lanes per warp pass, coalesced stores) and moves vals/cols.
+//
+// Layout written: vals[nnz] f64 and cols[nnz] i32 with element (step i, lane l) of a
+// chunk at start + 8*i + l -- the reference's layout (SURVEY.md 8a-R2 note (ii)).
+#include "cvr_internal.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// largest m in [lo, hi] with rd[m] <= key (the bisection of spmv.cpp:637-650, :655-667)
+template <typename RdT>
+__device__ __forceinline__ int64_t last_row_not_after(const RdT* __restrict__ rd, int64_t lo,
+                                                      int64_t hi, int64_t key)
+{
+    int64_t start = lo, stop = hi;
+    while (stop >= start) {
+        const int64_t mid = (stop + start) / 2;
+        if (key >= (int64_t)rd[mid]) start = mid + 1;
+        else stop = mid - 1;
+    }
+    return start - 1;
+}
+
+template <typename RdT>
+__global__ void __launch_bounds__(128)
+cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int32_t T,
+                    int32_t* __restrict__ record, CvrChunk* __restrict__ chunks,
+                    int2* __restrict__ segments, int32_t* __restrict__ seg_count)
+{
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+
+    // nnz-balanced slice of this chunk, multiples of 16 (spmv.cpp:584-586, :615-627)
+    const int64_t per = (nnz / T / 16) * 16;
+    const int64_t brk = (nnz - per * T) / 16;
+    int64_t s, e;
+    if (t < brk) {
+        s = t * (per + 16);
+        e = (t + 1) * (per + 16);
+    } else {
+        s = t * per + brk * 16;
+        e = (t + 1) * per + brk * 16;
+    }
+    if (t == T - 1) e = nnz;
+
+    const int64_t r0 = last_row_not_after(rd, 0, n_rows, s);      // :631-650
+    int64_t r1 = last_row_not_after(rd, r0, n_rows, e - 1);       // :652-667
+    while (r1 <= n_rows && rd[r1 + 1] == rd[r1]) r1++;            // :687-688 (degenerate tails only)
+    const int64_t span = r1 - r0 + 1;
+    const int32_t len = (int32_t)(e - s);
+    const int32_t n_steps = len / CVR_W;
+
+    int2* rec = reinterpret_cast<int2*>(record + cvr_record_offset(t, r0));
+    int2* seg = segments + cvr_segment_offset(t, r0);
+    int32_t n_rec = 0, n_seg = 0;
+
+    // lane trackers: vPack_valID / vPack_rowID / vPack_count / vPack_flag (:711-722)
+    int32_t src[CVR_W], row[CVR_W], left[CVR_W], from[CVR_W];
+    int64_t next_row = r0;
+#pragma unroll
+    for (int l = 0; l < CVR_W; l++) { // :727-759
+        if (next_row < r1) {
+            src[l] = (int32_t)((int64_t)rd[next_row] - s);
+            row[l] = (int32_t)next_row;
+            left[l] = (int32_t)(rd[next_row + 1] - rd[next_row]);
+        } else if (next_row == r1) {
+            src[l] = (int32_t)((int64_t)rd[next_row] - s);
+            row[l] = (int32_t)next_row;
+            left[l] = (int32_t)(e - (int64_t)rd[next_row]);
+        } else {
+            src[l] = row[l] = left[l] = 0;
+        }
+        if (l == 0) { // the first row may have begun in the previous chunk
+            src[0] = 0;
+            left[0] = (next_row == r1) ? len : (int32_t)((int64_t)rd[next_row + 1] - s);
+        }
+        from[l] = -1;
+        next_row++;
+    }
+
+    unsigned stolen = 0;  // first_flag (:796)
+    unsigned dirty = 0xffu; // lanes whose source offset was (re)set at the current step
+    bool tail_stored = false, stealing = false;
+    int32_t split0 = 0, split1 = 0;
+    int32_t tail[CVR_W];
+#pragma unroll
+    for (int l = 0; l < CVR_W; l++) tail[l] = 0;
+
+    int32_t i = 0;
+    while (i < n_steps) {
+        // ---- events of step i: every lane whose counter is 0, in lane order (:814-816)
+        for (int l = 0; l < CVR_W; l++) {
+            if (left[l] != 0) continue;
+            const int32_t pos = i * CVR_W + l;
+            if (next_row <= r1) {
+                // feeding (:821-868)
+                if (row[l] == (int32_t)r0) {
+                    split0 = pos;
+                } else {
+                    rec[n_rec++] = make_int2(pos, row[l]);
+                }
+                while (rd[next_row + 1] == rd[next_row]) next_row++; // skip empty rows
+                src[l] = (int32_t)((int64_t)rd[next_row] - s);
+                row[l] = (int32_t)next_row;
+                left[l] = (int32_t)(rd[next_row + 1] - rd[next_row]);
+                if (next_row == r1) {
+                    if (split1 == 0) split1 = pos;
+                    left[l] = (int32_t)(e - (int64_t)rd[next_row]);
+                    for (int q = 0; q < CVR_W; q++) tail[q] = row[q];
+                    tail_stored = true;
+                    for (int q = 0; q < CVR_W; q++)
+                        if (left[q] == 0) from[q] = 0; // :855-856
+                }
+                next_row++;
+            } else {
+                // stealing (:869-943): split the first lane that holds more than the average
+                int32_t total = 0;
+                for (int q = 0; q < CVR_W; q++) total += left[q];
+                const int32_t ave = total / CVR_W;
+                int victim = 0;
+                while (victim < CVR_W - 1 && !(left[victim] > ave)) victim++;
+                if (!((stolen >> l) & 1u)) {
+                    if (!stealing) {
+                        if (split1 == 0) split1 = (span <= CVR_W) ? -1 : pos;
+                        for (int q = 0; q < CVR_W; q++) tail[q] = row[q];
+                        tail_stored = true;
+                        stealing = true;
+                    }
+                    rec[n_rec++] = make_int2(pos, l);
+                    stolen |= 1u << l;
+                } else {
+                    rec[n_rec++] = make_int2(pos, from[l]); // :904-909, unreachable (SURVEY 8a-R2 note i)
+                }
+                from[l] = victim;
+                src[l] = src[victim];
+                row[l] = victim;
+                left[l] = ave;
+                left[victim] -= ave;
+                src[victim] += ave;
+                dirty |= 1u << victim;
+            }
+            dirty |= 1u << l;
+        }
+        // ---- one segment entry per lane that changed its source at this step
+        for (int l = 0; l < CVR_W; l++)
+            if ((dirty >> l) & 1u) seg[n_seg++] = make_int2(i * CVR_W + l, src[l]);
+        dirty = 0;
+
+        // ---- jump to the next step at which some lane runs empty
+        int32_t m = left[0];
+#pragma unroll
+        for (int l = 1; l < CVR_W; l++) m = min(m, left[l]);
+        if (m <= 0 || m >= n_steps - i) break;
+#pragma unroll
+        for (int l = 0; l < CVR_W; l++) {
+            src[l] += m;
+            left[l] -= m;
+        }
+        i += m;
+    }
+
+    // the eight terminators written inside the last step (:982-999)
+    for (int l = 0; l < CVR_W; l++) rec[n_rec + l] = make_int2(-1, from[l] == -1 ? l : from[l]);
+    // The reference leaves final_2 unwritten when a chunk never fed its last row nor stole
+    // (span <= 8 and all lanes end together); its kernel then reads garbage.  Store the
+    // intended rows instead.
+    if (!tail_stored)
+        for (int q = 0; q < CVR_W; q++) tail[q] = row[q];
+
+    CvrChunk c;
+    c.start = s;
+    c.len = len;
+    c.first_row = (int32_t)r0;
+    c.last_row = (int32_t)r1;
+    c.split0 = split0;
+    c.split1 = split1;
+    c.n_rec = n_rec;
+#pragma unroll
+    for (int q = 0; q < CVR_W; q++) c.tail[q] = tail[q];
+    chunks[t] = c;
+    seg_count[t] = n_seg;
+}
+
+// One warp per chunk; thread `lane_id` owns CVR element 32k + lane_id of window k, i.e.
+// step 4k + (lane_id >> 3), SIMD lane (lane_id & 7).
+__global__ void __launch_bounds__(128)
+cvr_permute_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
+                   const int2* __restrict__ segments, const int32_t* __restrict__ seg_count,
+                   const double* __restrict__ csr_val, const int32_t* __restrict__ csr_col,
+                   double* __restrict__ out_val, int32_t* __restrict__ out_col)
+{
+    const int32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chunk >= T) return;
+    const int t = threadIdx.x & 31;
+    const int j = t >> 3, l = t & 7;
+    const unsigned lt_mask = (1u << t) - 1u;
+
+    const int64_t start = chunks[chunk].start;
+    const int32_t len = chunks[chunk].len;
+    const int2* seg = segments + cvr_segment_offset(chunk, chunks[chunk].first_row);
+    const int32_t n_ent = seg_count[chunk];
+
+    const double* in_val = csr_val + start;
+    const int32_t* in_col = csr_col + start;
+    double* o_val = out_val + start;
+    int32_t* o_col = out_col + start;
+
+    int32_t eb = 0, ec = 0; // batch base / entries consumed
+    int2 held = (t < n_ent) ? seg[t] : make_int2(CVR_SEG_END, 0);
+    int32_t last_pos = __shfl_sync(FULL, held.x, 31);
+    int32_t base = 0; // source offset of my SIMD lane at the first step of the window
+
+    const int32_t n_win = (len + CVR_WIN - 1) / CVR_WIN;
+    for (int32_t k = 0; k < n_win; k++) {
+        const int32_t wstart = k * CVR_WIN;
+        if (ec != eb && last_pos < wstart + CVR_WIN) { // batch may not cover this window
+            eb = ec;
+            held = (eb + t < n_ent) ? seg[eb + t] : make_int2(CVR_SEG_END, 0);
+            last_pos = __shfl_sync(FULL, held.x, 31);
+        }
+        const unsigned rel = (unsigned)(held.x - wstart);
+        const unsigned flags = __reduce_or_sync(FULL, rel < 32u ? (1u << rel) : 0u);
+        int32_t src;
+        if (flags == 0) {
+            src = base + j;
+            base += 4;
+        } else {
+            const int rank = __popc(flags & lt_mask);
+            const int32_t mine = __shfl_sync(FULL, held.y, (ec - eb + rank) & 31);
+            const unsigned lane_bits = flags & (0x01010101u << l);
+            const unsigned upto = lane_bits & ((2u << t) - 1u);
+            const int t_src = upto ? 31 - __clz(upto) : t;
+            const int32_t got = __shfl_sync(FULL, mine, t_src);
+            src = upto ? got + ((t - t_src) >> 3) : base + j;
+            const int t_last = lane_bits ? 31 - __clz(lane_bits) : t;
+            const int32_t got_last = __shfl_sync(FULL, mine, t_last);
+            base = lane_bits ? got_last + 4 - (t_last >> 3) : base + 4;
+            ec += __popc(flags);
+        }
+        const int32_t p = wstart + t;
+        if (p < len) {
+            o_val[p] = in_val[src];
+            o_col[p] = in_col[src];
+        }
+    }
+}
+
+} // namespace
+
+int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream)
+{
+    const int threads = 128;
+    const int sched_blocks = (a.n_chunks + threads - 1) / threads;
+    if (a.rd64)
+        cvr_schedule_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
+            a.rd64, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+    else
+        cvr_schedule_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
+            a.rd32, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    const int64_t warps = a.n_chunks;
+    const int perm_blocks = (int)((warps * 32 + threads - 1) / threads);
+    cvr_permute_kernel<<<perm_blocks, threads, 0, stream>>>(a.chunks, a.n_chunks, a.segments,
+                                                            a.seg_count, a.csr_val, a.csr_col,
+                                                            a.cvr_vals, a.cvr_cols);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return 2;
+}

@@ -1,0 +1,64 @@
+// Internal declarations shared by the CUDA translation units of libcvr_b200.
+// Not part of the ABI (include/cvr_b200.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CVR_W 8              // lanes per step, fixed by the bit-exact contract (spmv.cpp:43)
+#define CVR_WIN 32           // one warp covers 4 steps x 8 lanes = 32 consecutive CVR elements
+#define CVR_SEG_STRIDE 48    // scratch segment entries reserved per chunk on top of its row span
+#define CVR_SEG_END 0x7fffffff
+
+// Per-chunk descriptor kept on the device: everything the reference keeps in
+// vPack_nnz_rows[4], vPack_split[2] and vPack_vec_final_2[8] for one OpenMP
+// thread (spmv.cpp:690-694, :826-891, :853/:893), with a 64-bit start offset.
+// 64 bytes, one per chunk.
+struct __align__(16) CvrChunk {
+    int64_t start;     // first element of the chunk in vals/cols   (nnz_rows[4t])
+    int32_t len;       // elements in the chunk, multiple of 16     (nnz_rows[4t+1] - start)
+    int32_t first_row; // nnz_rows[4t+2]
+    int32_t last_row;  // nnz_rows[4t+3]
+    int32_t split0;    // vPack_split[2t]   position where the (shared) first row ended, 0 = never
+    int32_t split1;    // vPack_split[2t+1] last feeding position, -1 = steal-only chunk, 0 = no event
+    int32_t n_rec;     // record pairs before the eight pos=-1 terminators
+    int32_t tail[CVR_W]; // vPack_vec_final_2[16t .. 16t+7]
+};
+static_assert(sizeof(CvrChunk) == 64, "CvrChunk must stay one 64-byte line");
+
+// int offset of chunk t's record region in the reference layout (spmv.cpp:709)
+__host__ __device__ inline int64_t cvr_record_offset(int64_t chunk, int64_t first_row)
+{
+    return (2 * (32 * chunk + first_row)) / 16 * 16;
+}
+
+// entry offset of chunk t's scratch segment list (conversion only)
+__host__ __device__ inline int64_t cvr_segment_offset(int64_t chunk, int64_t first_row)
+{
+    return CVR_SEG_STRIDE * chunk + first_row;
+}
+
+struct CvrConvertArgs {
+    // CSR on the device (1-based, n_rows+2 delimiters); one of rd32 / rd64
+    const double* csr_val;
+    const int32_t* csr_col;
+    const int32_t* rd32;
+    const int64_t* rd64;
+    int64_t nnz;
+    int64_t n_rows;
+    int32_t n_chunks;
+    // outputs
+    double* cvr_vals;
+    int32_t* cvr_cols;
+    int32_t* record;   // reference layout, pre-filled with 0xff
+    CvrChunk* chunks;
+    // scratch
+    int2* segments;    // (pos, src) entries, CVR_SEG_STRIDE*T + n_rows + slack
+    int32_t* seg_count;
+};
+
+// Launchers (each returns the number of kernels it launched, or <0 on launch failure)
+int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream);
+int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals,
+                    const int32_t* cols, const int32_t* record, const double* x, double* y,
+                    int64_t n_rows, cudaStream_t stream);

@@ -1,0 +1,162 @@
+"""Host-side mirror of the reference's function-level interface for the hot path.
+
+The reference exposes three functions to its main():
+  readMatrix(...)            spmv.cpp:311   -> cvr_b200.read_matrix
+  pre_processing(...)        spmv.cpp:565   -> cvr_b200.pre_processing  / CvrMatrix(...)
+  spmv_compute_kernel(...)   spmv.cpp:1016  -> cvr_b200.spmv_compute_kernel / CvrMatrix.spmv
+
+Everything here is a thin wrapper over the C ABI (include/cvr_b200.h); the arithmetic runs in
+the CUDA kernels of libcvr_b200.so.  Without that library, or without a GPU, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .csr import CsrMatrix
+
+
+def _ptr(a) -> int:
+    """Raw address of a numpy array, a torch tensor, or an int."""
+    if a is None:
+        return 0
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class DeviceCsr:
+    """A CSR whose arrays live on a CUDA device as torch tensors (val f64, col i32,
+    row_delim i32 or i64), same conventions as CsrMatrix.  Produced by cvr_b200.gen."""
+
+    def __init__(self, n_rows, n_cols, val, col, row_delim, nnz_true=None):
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.val, self.col, self.row_delim = val, col, row_delim
+        self.nnz = int(val.shape[0])
+        self.nnz_true = int(nnz_true) if nnz_true is not None else self.nnz
+
+    @property
+    def device(self):
+        return self.val.device
+
+    def to_host(self) -> CsrMatrix:
+        return CsrMatrix(self.n_rows, self.n_cols, self.val.cpu().numpy(), self.col.cpu().numpy(),
+                         self.row_delim.cpu().numpy(), self.nnz_true)
+
+
+class CvrMatrix:
+    """A matrix converted to CVR and resident on one GPU.  Construction = pre_processing."""
+
+    def __init__(self, csr, n_chunks: int = 0, device: int = 0):
+        lib = _lib.load()
+        self._lib = lib
+        self._h = C.c_void_p()
+        desc = _lib.CvrCsr()
+        desc.n_rows, desc.n_cols, desc.nnz = csr.n_rows, csr.n_cols, csr.nnz
+        desc.val, desc.col = _ptr(csr.val), _ptr(csr.col)
+        rd = csr.row_delim
+        wide = (rd.dtype == np.int64) if isinstance(rd, np.ndarray) else ("int64" in str(rd.dtype))
+        desc.row_delim32 = 0 if wide else _ptr(rd)
+        desc.row_delim64 = _ptr(rd) if wide else 0
+        if isinstance(csr, DeviceCsr):
+            if csr.device.type != "cuda":
+                raise ValueError("DeviceCsr must live on a CUDA device (no CPU path)")
+            device = csr.device.index if csr.device.index is not None else device
+            import torch
+            torch.cuda.synchronize(device)  # the generator's stream is not ours
+            rc = lib.cvr_create_from_device(C.byref(desc), int(n_chunks), int(device), C.byref(self._h))
+        else:
+            rc = lib.cvr_create(C.byref(desc), int(n_chunks), int(device), C.byref(self._h))
+        _lib.check(rc)
+        self.n_rows, self.n_cols, self.nnz = csr.n_rows, csr.n_cols, csr.nnz
+        self.nnz_true = getattr(csr, "nnz_true", csr.nnz)
+
+    # -- lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.cvr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- queries
+    @property
+    def info(self) -> dict:
+        i = _lib.CvrInfo()
+        _lib.check(self._lib.cvr_get_info(self._h, C.byref(i)))
+        return {name: getattr(i, name) for name, _ in _lib.CvrInfo._fields_}
+
+    @property
+    def n_chunks(self) -> int:
+        return self.info["n_chunks"]
+
+    def device_vectors(self):
+        x, y = C.c_void_p(), C.c_void_p()
+        _lib.check(self._lib.cvr_device_vectors(self._h, C.byref(x), C.byref(y)))
+        return x.value, y.value
+
+    # -- the hot path
+    def spmv(self, x, iters: int = 1):
+        """spmv_compute_kernel with host vectors: returns (y[n_rows+1], seconds per iteration).
+        x has n_cols+1 entries (index 0 is the phantom column)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.shape[0] != self.n_cols + 1:
+            raise ValueError(f"x must have n_cols+1 = {self.n_cols + 1} entries")
+        y = np.empty(self.n_rows + 1, dtype=np.float64)
+        secs = C.c_double()
+        _lib.check(self._lib.cvr_spmv(self._h, x.ctypes.data, y.ctypes.data, int(iters), C.byref(secs)))
+        return y, secs.value
+
+    def spmv_into(self, x_host, y_host, iters: int = 1) -> float:
+        """Same call on caller-owned (e.g. pinned) host buffers given as raw addresses/arrays."""
+        secs = C.c_double()
+        _lib.check(self._lib.cvr_spmv(self._h, _ptr(x_host), _ptr(y_host), int(iters), C.byref(secs)))
+        return secs.value
+
+    def spmv_device(self, x_dev, y_dev, stream: int = 0) -> None:
+        """Enqueue one SpMV on device vectors (torch tensors or raw pointers) on `stream`."""
+        _lib.check(self._lib.cvr_spmv_device(self._h, _ptr(x_dev), _ptr(y_dev), int(stream)))
+
+    # -- the bit-exact gate
+    def export(self) -> dict:
+        """CVR structure arrays in the reference's layout and sizes (cvr_export)."""
+        info = self.info
+        T = info["n_chunks"]
+        out = {
+            "n_chunks": T,
+            "vals": np.empty(self.nnz, dtype=np.float64),
+            "cols": np.empty(self.nnz, dtype=np.int32),
+            "record": np.empty(info["record_ints"], dtype=np.int32),
+            "nnz_rows": np.empty(4 * T, dtype=np.int32),
+            "final_2": np.full(16 * T, -777777, dtype=np.int32),
+            "split": np.empty(2 * T, dtype=np.int32),
+        }
+        arr = _lib.CvrArrays(*(out[k].ctypes.data for k in ("vals", "cols", "record", "nnz_rows", "final_2", "split")))
+        _lib.check(self._lib.cvr_export(self._h, C.byref(arr)))
+        return out
+
+
+def pre_processing(csr, n_threads: int = 0, device: int = 0) -> CvrMatrix:
+    """CSR -> CVR on the GPU (spmv.cpp:565).  n_threads = number of chunks; 0 = auto."""
+    return CvrMatrix(csr, n_threads, device)
+
+
+def spmv_compute_kernel(cvr: CvrMatrix, x, n_times: int = 1):
+    """y = A x, n_times iterations (spmv.cpp:1016).  Returns (y, seconds per iteration)."""
+    return cvr.spmv(x, n_times)

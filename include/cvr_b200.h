@@ -1,0 +1,158 @@
+/* cvr_b200.h -- C ABI of the B200-native CVR SpMV path.
+ *
+ * This is the drop-in boundary for the one hot path of puckbee/CVR: the
+ * CSR -> CVR conversion and the CVR SpMV loop.  The reference has no library
+ * API; its main() (spmv.cpp:1675) calls two C++ functions with caller-owned
+ * buffers.  Each entry point below names the reference interface it replaces
+ * (all citations: /root/reference/spmv.cpp).  INTEGRATION.md shows the patch a
+ * maintainer of the reference would apply to call this library instead.
+ *
+ * Conventions (identical to the reference, SURVEY.md 8b "data conventions"):
+ *   - fp64 values, int32 column indices, 1-BASED rows and columns as
+ *     readMatrix leaves them (:437-438): row 0 / column 0 are phantoms.
+ *   - row_delim has n_rows+2 entries, row r occupies [row_delim[r], row_delim[r+1]).
+ *   - nnz is padded to a multiple of 16 (:457).
+ *   - x has n_cols+1 entries, y has n_rows+1 entries (index 0 unused / 0.0).
+ *   - n_chunks is the reference's numThreads: chunk t of the CVR layout is what
+ *     OpenMP thread t owns in the reference, so the structure arrays are
+ *     comparable bit for bit at equal n_chunks.
+ *
+ * Every function returns 0 on success or a negative cvr_status_t; the message
+ * is available from cvr_last_error() (thread-local).  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with
+ * CVR_ERR_CUDA.
+ */
+#ifndef CVR_B200_H
+#define CVR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVR_B200_ABI_VERSION 1
+#define CVR_LANES 8 /* SIMD_LEN for fp64, spmv.cpp:43 -- fixed by the bit-exact contract */
+
+typedef enum cvr_status {
+    CVR_OK = 0,
+    CVR_ERR_INVALID = -1, /* bad argument (NULL, nnz % 16, n_chunks > nnz/16, ...) */
+    CVR_ERR_CUDA = -2,    /* CUDA runtime failure, or no device */
+    CVR_ERR_RANGE = -3,   /* a value does not fit the int32 export layout */
+    CVR_ERR_STATE = -4    /* call order violated */
+} cvr_status_t;
+
+typedef struct cvr_handle cvr_handle_t;
+
+/* The CSR readMatrix produces (out-params of spmv.cpp:311-312).  Exactly one of
+ * row_delim32 / row_delim64 is non-NULL; the 64-bit form exists because the
+ * reference's `int` delimiters cannot address nnz >= 2^31. */
+typedef struct cvr_csr {
+    int64_t n_rows;
+    int64_t n_cols;
+    int64_t nnz;                /* padded, multiple of 16 */
+    const double* val;          /* [nnz]   h_val            */
+    const int32_t* col;         /* [nnz]   h_cols, 1-based  */
+    const int32_t* row_delim32; /* [n_rows+2] h_rowDelimiters, or NULL */
+    const int64_t* row_delim64; /* [n_rows+2], or NULL */
+} cvr_csr_t;
+
+/* Host buffers of the reference's own sizes (allocation at spmv.cpp:1793-1817)
+ * filled by cvr_export for the bit-exact gate.  Any pointer may be NULL to skip
+ * that array. */
+typedef struct cvr_arrays {
+    double* vals;      /* [nnz]                vPack_vec_vals   */
+    int32_t* cols;     /* [nnz]                vPack_vec_cols   */
+    int32_t* record;   /* [cvr_record_ints()]  vPack_vec_record, (pos,wb) pairs; chunk t's
+                          region starts at int offset (2*(32t+first_row))/16*16 (:709) */
+    int32_t* nnz_rows; /* [4*n_chunks]         vPack_nnz_rows: s, e, first_row, last_row */
+    int32_t* final_2;  /* [16*n_chunks]        vPack_vec_final_2: 8 tail rows used per chunk */
+    int32_t* split;    /* [2*n_chunks]         vPack_split */
+} cvr_arrays_t;
+
+typedef struct cvr_info {
+    int64_t n_rows, n_cols, nnz; /* nnz padded */
+    int32_t n_chunks;
+    int32_t device;
+    int64_t n_records;       /* (pos,wb) pairs incl. the 8 terminators per chunk */
+    int64_t record_ints;     /* size of the exported record array in ints */
+    int64_t algorithmic_bytes; /* per SpMV: 12*nnz + 8*n_records + 56*T + 8*(n_cols+1) + 8*(n_rows+1) */
+    double convert_seconds;  /* device conversion only (CUDA events) */
+    double create_seconds;   /* upload + conversion, host wall clock */
+    int64_t kernel_launches; /* kernels this handle has launched so far */
+    int64_t device_bytes;    /* device memory owned by the handle */
+} cvr_info_t;
+
+/* CSR owned by the library, produced by cvr_read_matrix_market. */
+typedef struct cvr_host_csr {
+    int64_t n_rows, n_cols;
+    int64_t nnz;      /* padded to a multiple of 16 */
+    int64_t nnz_file; /* entries before padding (mirrored entries included) */
+    double* val;
+    int32_t* col;
+    int32_t* row_delim32; /* set when nnz < 2^31, else NULL */
+    int64_t* row_delim64; /* set when nnz >= 2^31, else NULL */
+} cvr_host_csr_t;
+
+/* flags for cvr_read_matrix_market */
+#define CVR_MM_REF_LAST_DELIM 1 /* reproduce row_delim[k] = nnz-1 after the last row (spmv.cpp:522-526) */
+#define CVR_MM_KEEP_LAST_LINE 2 /* keep a final line that lacks '\n' (the reference drops it, :411) */
+
+int cvr_abi_version(void);
+const char* cvr_last_error(void);
+
+/* Create the CUDA context on `device` (so that later timings exclude it). */
+int cvr_device_init(int device);
+
+/* Replaces readMatrix (spmv.cpp:311-535): Matrix Market coordinate file -> the 1-based,
+ * x16-padded CSR described above, with the reference's observable ingest semantics
+ * (item 7, the off-by-one last delimiter, only on request).
+ * Host only.  Release with cvr_free_host_csr. */
+int cvr_read_matrix_market(const char* path, int flags, cvr_host_csr_t* out);
+void cvr_free_host_csr(cvr_host_csr_t* csr);
+
+/* ints in the record array for (n_rows, n_chunks): 2*(n_rows+240+32*n_chunks), spmv.cpp:1806 */
+int64_t cvr_record_ints(int64_t n_rows, int32_t n_chunks);
+
+/* A chunk count that fills `device` (multiple of the SM count, ~KBs of stream per
+ * chunk).  What `numThreads = 0` means on the command line. */
+int cvr_auto_chunks(int64_t nnz, int device, int32_t* n_chunks);
+
+/* Replaces pre_processing (spmv.cpp:565, called at :1857): uploads the host CSR
+ * to `device`, converts it there and keeps the CVR arrays on the device.
+ * n_chunks <= nnz/16 (note (v) of SURVEY 8a-R2); n_chunks == 0 picks cvr_auto_chunks. */
+int cvr_create(const cvr_csr_t* csr_host, int32_t n_chunks, int device, cvr_handle_t** out);
+
+/* Same, for a CSR already resident on `device` (device pointers in `csr_dev`):
+ * the entry the multi-GPU host and the synthetic generators use.  The CSR is
+ * only read during the call. */
+int cvr_create_from_device(const cvr_csr_t* csr_dev, int32_t n_chunks, int device,
+                           cvr_handle_t** out);
+
+/* Replaces spmv_compute_kernel (spmv.cpp:1016, called at :1882) with HOST
+ * vectors: copies x (n_cols+1) in, runs `iters` SpMVs (each zeroes y inside the
+ * timed region, unlike spmv.cpp:1026-1033), copies y (n_rows+1) out.
+ * seconds_per_iter (optional) is the device time of the iteration loop / iters,
+ * the quantity the reference prints at :1662. */
+int cvr_spmv(cvr_handle_t* h, const double* x_host, double* y_host, int32_t iters,
+             double* seconds_per_iter);
+
+/* One SpMV on device vectors, enqueued on `cuda_stream` (a cudaStream_t, NULL =
+ * default stream) without synchronising: y_dev[0..n_rows] = A * x_dev. */
+int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* cuda_stream);
+
+/* Bit-exact gate: copy the CVR structure arrays back in the reference layout. */
+int cvr_export(cvr_handle_t* h, cvr_arrays_t* host_out);
+
+int cvr_get_info(cvr_handle_t* h, cvr_info_t* info);
+
+/* Device pointers of the handle's x / y scratch vectors (n_cols+1 / n_rows+1
+ * doubles), for callers that iterate on the device. */
+int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev);
+
+void cvr_destroy(cvr_handle_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVR_B200_H */
