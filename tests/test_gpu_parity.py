@@ -1,0 +1,181 @@
+"""GPU suite (B200): the CUDA path through the C ABI against the oracle.
+
+* structure arrays: bit-exact against the reference fixtures (tests/golden) and against the
+  oracle port on generated matrices, at several chunk counts;
+* y: per-row |dy| <= 1e-12 * sum|a x| against the reference's scalar CSR loop (oracle port);
+* edge cases: steal-only chunks, empty rows, one chunk, the largest legal chunk count,
+  a chunk that never stores its tail, non-square matrices;
+* full-size properties: linearity and a checksum at a size the oracle would take long on.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import (GOLDEN, assert_structure_equal, assert_y_close, golden_cases, golden_structure,
+                     load_golden, to_oracle_csr)
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cvr(native_lib):
+    import cvr_b200
+    return cvr_b200
+
+
+def host_csr(cvr, c):
+    return cvr.CsrMatrix(c.n_rows, c.n_cols, c.val, c.col, c.row_delim, c.nnz_file)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_structure_bit_exact_vs_reference_fixture(cvr, name):
+    z, csr = load_golden(name)
+    for T in z["chunk_counts"]:
+        T = int(T)
+        with cvr.CvrMatrix(host_csr(cvr, csr), T) as m:
+            assert_structure_equal(m.export(), golden_structure(z, T), f"{name} T={T}")
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_y_within_tolerance_on_fixtures(cvr, name):
+    z, csr = load_golden(name)
+    x = z["x"]
+    for T in z["chunk_counts"]:
+        with cvr.CvrMatrix(host_csr(cvr, csr), int(T)) as m:
+            y, secs = m.spmv(x, iters=3)  # repeated: y is re-zeroed every iteration
+            assert secs > 0
+            assert_y_close(y, csr, x, f"{name} T={T}")
+
+
+def test_kat12_through_the_abi(cvr):
+    m = cvr.read_matrix(os.path.join(GOLDEN, "kat12.mtx"))
+    want_y = [0, 315, 207, 0, 807, 2534, 607, 710, 3222, 1813, 1007, 6639, 7233]
+    for T in (1, 2):
+        with cvr.CvrMatrix(m, T) as a:
+            y, _ = a.spmv(np.ones(13))
+            assert y.tolist() == want_y
+            e = a.export()
+            if T == 1:
+                assert e["split"].tolist() == [0, 14]
+                assert e["final_2"][:8].tolist() == [1, 10, 9, 4, 5, 11, 12, 8]
+
+
+GENERATED = {
+    "rand": (lambda g: g.random_sparse(20000, 15000, 150000, seed=41, empty_frac=0.25), [1, 7, 64, 1000, 5000]),
+    "long": (lambda g: g.random_sparse(3000, 3000, 9000, seed=42, long_rows=6, long_len=2500), [1, 16, 300, 1400]),
+    "web": (lambda g: g.powerlaw_web(60000, 330000, seed=43), [8, 592, 4736]),
+    "fem": (lambda g: g.fem27(20, 20, 20), [3, 148, 2000]),
+    "rmat": (lambda g: g.rmat(14, 16, seed=44), [5, 1184, 9000]),
+    "road": (lambda g: g.road(200000, seed=45), [2, 500, 8000]),
+}
+
+
+@pytest.mark.parametrize("name", list(GENERATED))
+def test_generated_matrices_vs_oracle_port(cvr, name):
+    from cvr_b200 import gen
+    make, Ts = GENERATED[name]
+    d = make(gen)
+    csr = to_oracle_csr(d)
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-1, 1, csr.n_cols + 1)
+    for T in Ts:
+        T = min(T, csr.nnz // 16)
+        want = oracle.convert(csr, T, "port", fill_missing_tail=True)
+        with cvr.CvrMatrix(d.to_host(), T) as m:
+            assert_structure_equal(m.export(), want, f"{name} T={T}")
+            y, _ = m.spmv(x)
+            assert_y_close(y, csr, x, f"{name} T={T}")
+            y1, _ = m.spmv(np.ones(csr.n_cols + 1))
+            assert_y_close(y1, csr, np.ones(csr.n_cols + 1), f"{name} T={T} x=1")
+
+
+def test_maximum_chunk_count_and_single_chunk(cvr):
+    from cvr_b200 import gen
+    d = gen.random_sparse(500, 700, 4000, seed=46, empty_frac=0.1)
+    csr = to_oracle_csr(d)
+    x = np.random.default_rng(3).uniform(-1, 1, csr.n_cols + 1)
+    for T in (1, csr.nnz // 16):  # every chunk holds exactly 16 elements at the maximum
+        with cvr.CvrMatrix(d.to_host(), T) as m:
+            assert_structure_equal(m.export(), oracle.convert(csr, T, "port", fill_missing_tail=True), f"T={T}")
+            y, _ = m.spmv(x)
+            assert_y_close(y, csr, x, f"T={T}")
+    with pytest.raises(cvr.CvrError):
+        cvr.CvrMatrix(d.to_host(), csr.nnz // 16 + 1)
+
+
+def test_auto_chunks_and_device_csr_entry(cvr):
+    import torch
+    from cvr_b200 import gen
+    d = gen.fem27(30, 30, 30, device="cuda")
+    csr = to_oracle_csr(d)
+    x = np.random.default_rng(4).uniform(-1, 1, csr.n_cols + 1)
+    with cvr.CvrMatrix(d, 0) as m:  # n_chunks = 0: cvr_auto_chunks, CSR already on the device
+        info = m.info
+        assert info["n_chunks"] % torch.cuda.get_device_properties(0).multi_processor_count == 0
+        assert info["kernel_launches"] == 2
+        want = oracle.convert(csr, info["n_chunks"], "port", fill_missing_tail=True)
+        assert_structure_equal(m.export(), want, "auto")
+        y, _ = m.spmv(x)
+        assert_y_close(y, csr, x, "auto")
+        # device-vector entry on a torch stream
+        xd = torch.from_numpy(x).cuda()
+        yd = torch.full((csr.n_rows + 1,), 7.0, dtype=torch.float64, device="cuda")
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        m.spmv_device(xd, yd, s.cuda_stream)
+        s.synchronize()
+        assert_y_close(yd.cpu().numpy(), csr, x, "spmv_device")
+        assert m.info["algorithmic_bytes"] == (12 * csr.nnz + 8 * info["n_records"] + 56 * info["n_chunks"]
+                                               + 8 * (csr.n_cols + 1) + 8 * (csr.n_rows + 1))
+
+
+def test_full_size_properties_linearity_and_checksum(cvr):
+    """Config-2-sized input (1M rows, 26.5M nnz): too slow for the scalar port in a unit test,
+    so check size-independent properties: A(ax+by) = aAx + bAy row by row within the bound, and
+    sum(y) against a torch fp64 CSR reference computed on the device."""
+    import torch
+    from cvr_b200 import gen
+    d = gen.fem27(100, 100, 100, device="cuda")
+    n = d.n_rows
+    with cvr.CvrMatrix(d, 0) as m:
+        g = torch.Generator(device="cuda").manual_seed(1)
+        x1 = torch.rand(n + 1, generator=g, device="cuda", dtype=torch.float64) - 0.5
+        x2 = torch.rand(n + 1, generator=g, device="cuda", dtype=torch.float64) - 0.5
+        ys = []
+        for xv in (x1, x2, 2.0 * x1 - 3.0 * x2):
+            y = torch.empty(n + 1, dtype=torch.float64, device="cuda")
+            m.spmv_device(xv, y, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            ys.append(y)
+        rd = d.row_delim.to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(n + 1, device="cuda"), rd[1:] - rd[:-1])
+        prod = d.val * x1[d.col.long()]
+        y_ref = torch.zeros(n + 1, dtype=torch.float64, device="cuda").index_add_(0, rows, prod)
+        mag = torch.zeros(n + 1, dtype=torch.float64, device="cuda").index_add_(0, rows, prod.abs())
+        assert bool(((ys[0] - y_ref).abs() <= 1e-12 * mag + 1e-300).all())
+        lin = (ys[2] - (2.0 * ys[0] - 3.0 * ys[1])).abs()
+        assert bool((lin <= 1e-11 * (mag + 1.0)).all())
+        assert abs(float(ys[0].sum() - y_ref.sum())) <= 1e-9 * float(mag.sum())
+
+
+def test_cli_prints_the_reference_lines(cvr, tmp_path):
+    from cvr_b200 import gen, write_mtx
+    d = gen.powerlaw_web(5000, 30000, seed=47).to_host()
+    rows = d.row_of_entry()
+    keep = np.arange(d.nnz) < d.nnz  # padding zeros are written too: harmless explicit zeros
+    p = str(tmp_path / "web.mtx")
+    write_mtx(p, d.n_rows, d.n_cols, rows[keep], d.col[keep], d.val[keep])
+    cli = os.path.join(ROOT, "cvr_b200", "bin", "spmv.cvr")
+    out = subprocess.run([cli, p, "64", "10"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.splitlines()
+    for pat in ("Pre-processing", "SpMV Execution", "Throughput"):  # README.md:47-49 greps
+        assert sum(pat in ln for ln in lines) == 1, pat
+    assert any(ln.startswith("The Pre-processing(CSR->CVR)   Time of CVR   is ") and "[threads: 64]" in ln for ln in lines)
+    assert any(ln.startswith("The SpMV Execution Time of CVR    is ") for ln in lines)
+    assert any(ln.startswith("         The Throughput of CVR    is ") and "GFlops." in ln for ln in lines)
+    assert "     Very Good! Your result is correct  " in lines
