@@ -62,6 +62,10 @@ struct cvr_handle {
     int64_t launches = 0;
     int64_t device_bytes = 0;
     std::vector<CvrChunk> host_chunks; // copy of the descriptors (export / info)
+    // optional per-launch timing of the SpMV kernel alone (cvr_set_kernel_timing)
+    bool timing = false;
+    std::vector<cudaEvent_t> timing_events; // begin/end pairs, `timing_used` of them recorded
+    size_t timing_used = 0;
 
     ~cvr_handle()
     {
@@ -74,6 +78,7 @@ struct cvr_handle {
         cudaFree(y);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t e : timing_events) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -319,9 +324,22 @@ int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* c
 {
     if (!h || !x_dev || !y_dev) return fail(CVR_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    cudaEvent_t eb = nullptr, ee = nullptr;
+    if (h->timing) {
+        if (h->timing_used + 2 > h->timing_events.size()) {
+            for (int k = 0; k < 2; k++) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreate(&e));
+                h->timing_events.push_back(e);
+            }
+        }
+        eb = h->timing_events[h->timing_used];
+        ee = h->timing_events[h->timing_used + 1];
+        h->timing_used += 2;
+    }
     const int launched = cvr_launch_spmv(h->chunks, h->n_chunks, h->vals, h->cols, h->record,
                                          x_dev, y_dev, h->n_rows,
-                                         static_cast<cudaStream_t>(cuda_stream));
+                                         static_cast<cudaStream_t>(cuda_stream), eb, ee);
     if (launched < 0)
         return fail(CVR_ERR_CUDA, "SpMV launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += launched;
@@ -408,6 +426,31 @@ int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev)
     if (!h) return fail(CVR_ERR_INVALID, "NULL handle");
     if (x_dev) *x_dev = h->x;
     if (y_dev) *y_dev = h->y;
+    return CVR_OK;
+}
+
+int cvr_set_kernel_timing(cvr_handle_t* h, int enabled)
+{
+    if (!h) return fail(CVR_ERR_INVALID, "NULL handle");
+    h->timing = enabled != 0;
+    h->timing_used = 0;
+    return CVR_OK;
+}
+
+int cvr_get_kernel_timing(cvr_handle_t* h, double* total_seconds, int64_t* launches)
+{
+    if (!h || !total_seconds || !launches) return fail(CVR_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    double total = 0.0;
+    for (size_t k = 0; k + 1 < h->timing_used; k += 2) {
+        CUDA_TRY(cudaEventSynchronize(h->timing_events[k + 1]));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->timing_events[k], h->timing_events[k + 1]));
+        total += (double)ms * 1e-3;
+    }
+    *total_seconds = total;
+    *launches = (int64_t)(h->timing_used / 2);
+    h->timing_used = 0;
     return CVR_OK;
 }
 

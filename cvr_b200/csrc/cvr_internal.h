@@ -59,6 +59,8 @@ struct CvrConvertArgs {
 
 // Launchers (each returns the number of kernels it launched, or <0 on launch failure)
 int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream);
+// ev_begin / ev_end (optional) bracket the SpMV kernel alone, after y has been cleared
 int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals,
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
-                    int64_t n_rows, cudaStream_t stream);
+                    int64_t n_rows, cudaStream_t stream, cudaEvent_t ev_begin = nullptr,
+                    cudaEvent_t ev_end = nullptr);

@@ -111,7 +111,7 @@ cvr_spmv_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
     if (chunk >= T) return;
     const int t = threadIdx.x & 31;
 
-    // chunk descriptor: 64 B, read as four 16 B words by lanes 0..3 and broadcast
+    // chunk descriptor: one 64 B line, every thread reads the same words (broadcast loads)
     const CvrChunk* cp = chunks + chunk;
     const int64_t start = cp->start;
     const int32_t len = cp->len;
@@ -192,13 +192,15 @@ cvr_spmv_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
 
 int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals,
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
-                    int64_t n_rows, cudaStream_t stream)
+                    int64_t n_rows, cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end)
 {
     if (cudaMemsetAsync(y, 0, sizeof(double) * (size_t)(n_rows + 1), stream) != cudaSuccess)
         return -1;
     const int threads = 128;
     const int blocks = (int)(((int64_t)n_chunks * 32 + threads - 1) / threads);
+    if (ev_begin) cudaEventRecord(ev_begin, stream);
     cvr_spmv_kernel<<<blocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
+    if (ev_end) cudaEventRecord(ev_end, stream);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return 1;
 }

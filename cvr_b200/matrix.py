@@ -133,6 +133,16 @@ class CvrMatrix:
         """Enqueue one SpMV on device vectors (torch tensors or raw pointers) on `stream`."""
         _lib.check(self._lib.cvr_spmv_device(self._h, _ptr(x_dev), _ptr(y_dev), int(stream)))
 
+    # -- measurement aid
+    def set_kernel_timing(self, enabled: bool) -> None:
+        _lib.check(self._lib.cvr_set_kernel_timing(self._h, int(enabled)))
+
+    def kernel_timing(self):
+        """(summed SpMV-kernel seconds, launches) since timing was enabled / last read."""
+        secs, n = C.c_double(), C.c_int64()
+        _lib.check(self._lib.cvr_get_kernel_timing(self._h, C.byref(secs), C.byref(n)))
+        return secs.value, n.value
+
     # -- the bit-exact gate
     def export(self) -> dict:
         """CVR structure arrays in the reference's layout and sizes (cvr_export)."""

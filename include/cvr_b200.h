@@ -150,6 +150,13 @@ int cvr_get_info(cvr_handle_t* h, cvr_info_t* info);
  * doubles), for callers that iterate on the device. */
 int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev);
 
+/* Measurement aid: while enabled, every SpMV launch is bracketed by a CUDA event pair on
+ * its stream (after y has been cleared), so the SpMV kernel's own device time can be
+ * reported next to the whole-step time.  cvr_get_kernel_timing waits for the recorded
+ * launches, returns their summed kernel time and count, and resets the counters. */
+int cvr_set_kernel_timing(cvr_handle_t* h, int enabled);
+int cvr_get_kernel_timing(cvr_handle_t* h, double* total_seconds, int64_t* launches);
+
 void cvr_destroy(cvr_handle_t* h);
 
 #ifdef __cplusplus
