@@ -27,6 +27,9 @@
 // stream, inside the timed region).
 #include "cvr_internal.h"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -102,7 +105,7 @@ __device__ __forceinline__ void flush_window(WarpState& st, const int2* __restri
 }
 
 __global__ void __launch_bounds__(128)
-cvr_spmv_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
+cvr_spmv_window_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
                 const double* __restrict__ vals, const int32_t* __restrict__ cols,
                 const int32_t* __restrict__ record, const double* __restrict__ x,
                 double* __restrict__ y)
@@ -188,6 +191,179 @@ cvr_spmv_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tile walker (the default kernel).
+//
+// ncu on the window kernel above (profiles/r01_v0_*) showed it instruction-bound: with ~27
+// nnz per row some lane switches rows in 3 of 4 windows, so nearly every window paid the
+// warp-wide segmented reduction (82 warp-instructions per 32 nnz, 43 % issue utilisation,
+// 2.1 TB/s).  Here a warp still owns one chunk, but a pass covers a TILE of 32 steps x 8
+// lanes = 256 elements and thread t = (q, l) walks EIGHT CONSECUTIVE steps of SIMD lane l:
+// steps 8q .. 8q+7 of the tile.  A row switch is then a thread-local event (emit the
+// accumulator, clear it); threads of the same SIMD lane only meet once per tile, in a
+// 3-shuffle carry chain that hands the open partial sum from walker q to walker q+1.
+//   * loads: for each of the 8 steps a warp load touches 4 x 64 B (vals) / 4 x 32 B (cols)
+//     fully used sectors; all 16 loads of a tile are issued before the first use.
+//   * records are delivered to their owner thread through shared memory: the warp holds 32
+//     records in registers (coalesced 256 B load), each holder drops a flag byte and the
+//     write-back target into the owner's slot.
+// ---------------------------------------------------------------------------------------
+constexpr int TB = 8;                 // consecutive steps per walker
+constexpr int TILE = 4 * TB * CVR_W;  // 256 elements per warp pass
+constexpr int WARPS = 4;              // warps per block
+constexpr int32_t WB_SPLIT0 = -2;     // marker: flush into the shared first row
+
+struct TileCtx {
+    double* __restrict__ y;
+    const int32_t* tail;
+    int32_t split1, first_row;
+    int l;
+};
+
+__device__ __forceinline__ void emit(const TileCtx& cx, double value, int32_t pos, int32_t wb,
+                                     double& carry_slot)
+{
+    if (wb == WB_SPLIT0) atomicAdd(&cx.y[cx.first_row], value);            // spmv.cpp:1280-1282
+    else if (cx.split1 != -1 && pos <= cx.split1) cx.y[wb] = value;        // feeding, :1204
+    else if (wb == cx.l) carry_slot += value;                              // stealing, :1541
+    else if (cx.tail[wb] != 0) atomicAdd(&cx.y[cx.tail[wb]], value);       // (unreachable)
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+cvr_spmv_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
+                const double* __restrict__ vals, const int32_t* __restrict__ cols,
+                const int32_t* __restrict__ record, const double* __restrict__ x,
+                double* __restrict__ y)
+{
+    __shared__ unsigned long long s_flags[WARPS][32]; // 8 flag bytes per thread (one per step)
+    __shared__ int32_t s_wb[WARPS][TB][32];           // write-back target per (step, thread)
+
+    const int32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chunk >= T) return;
+    const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = t >> 3, l = t & 7;
+
+    const CvrChunk* cp = chunks + chunk;
+    const int64_t start = cp->start;
+    const int32_t len = cp->len;
+    const int32_t split0 = cp->split0;
+    const int32_t n_rec = cp->n_rec;
+    TileCtx cx;
+    cx.y = y;
+    cx.tail = cp->tail;
+    cx.split1 = cp->split1;
+    cx.first_row = cp->first_row;
+    cx.l = l;
+
+    const int2* rec = reinterpret_cast<const int2*>(record + cvr_record_offset(chunk, cx.first_row));
+    const double* v = vals + start;
+    const int32_t* c = cols + start;
+
+    s_flags[w][t] = 0ull;
+    int32_t rb = 0;
+    int2 held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
+    double lane_carry = 0.0; // open partial sum of SIMD lane l at the tile boundary
+    double carry_slot = 0.0; // private share of t_rets[l] (spmv.cpp:1124)
+    __syncwarp();
+
+    const int32_t n_tiles = (len + TILE - 1) / TILE;
+    for (int32_t tile = 0; tile < n_tiles; tile++) {
+        const int32_t ts = tile * TILE;
+        const int32_t p0 = ts + q * (TB * CVR_W) + l; // my element of step 8q; next step: +8
+
+        double a[TB], xv[TB];
+        int32_t ci[TB];
+#pragma unroll
+        for (int b = 0; b < TB; b++) {
+            const int32_t p = p0 + b * CVR_W;
+            const bool in = p < len;
+            a[b] = in ? ld_stream_f64(v + p) : 0.0;
+            ci[b] = in ? ld_stream_s32(c + p) : 0;
+        }
+#pragma unroll
+        for (int b = 0; b < TB; b++) xv[b] = __ldg(x + ci[b]);
+
+        // ---- deliver the records of this tile to their owner threads
+        for (;;) {
+            const uint32_t rel = (uint32_t)(held.x - ts);
+            if (rel < (uint32_t)TILE) {
+                const uint32_t step = rel >> 3;
+                const uint32_t owner = (step >> 3) * CVR_W + (rel & 7u);
+                reinterpret_cast<unsigned char*>(&s_flags[w][owner])[step & 7u] = 1;
+                s_wb[w][step & 7u][owner] = held.y;
+            }
+            const int32_t last = __shfl_sync(FULL, held.x, 31);
+            if ((uint32_t)last >= (uint32_t)(ts + TILE)) break; // batch reaches past the tile (or ended)
+            rb += 32;
+            held = (rb + t < n_rec) ? rec[rb + t] : make_int2(-1, 0);
+        }
+        if (t == 0 && split0 != 0) {
+            const uint32_t rel = (uint32_t)(split0 - ts);
+            if (rel < (uint32_t)TILE) {
+                const uint32_t step = rel >> 3;
+                const uint32_t owner = (step >> 3) * CVR_W + (rel & 7u);
+                reinterpret_cast<unsigned char*>(&s_flags[w][owner])[step & 7u] = 1;
+                s_wb[w][step & 7u][owner] = WB_SPLIT0;
+            }
+        }
+        __syncwarp();
+        const unsigned long long f = s_flags[w][t];
+
+        // ---- walk my eight steps; the first flush waits for the carry of earlier walkers
+        double acc = 0.0, head = 0.0;
+        int first_b = -1;
+        if (f == 0ull) {
+#pragma unroll
+            for (int b = 0; b < TB; b++) acc = fma(a[b], xv[b], acc);
+        } else {
+            s_flags[w][t] = 0ull;
+#pragma unroll
+            for (int b = 0; b < TB; b++) {
+                if ((f >> (8 * b)) & 1ull) {
+                    if (first_b < 0) {
+                        head = acc;
+                        first_b = b;
+                    } else {
+                        emit(cx, acc, p0 + b * CVR_W, s_wb[w][b][t], carry_slot);
+                    }
+                    acc = 0.0;
+                }
+                acc = fma(a[b], xv[b], acc);
+            }
+        }
+        const bool has = first_b >= 0;
+        double cin = (q == 0) ? lane_carry : 0.0;
+        double out = has ? acc : cin + acc;
+#pragma unroll
+        for (int r = 1; r < 4; r++) {
+            const double prev = __shfl_up_sync(FULL, out, CVR_W);
+            if (q == r) {
+                cin = prev;
+                out = has ? acc : cin + acc;
+            }
+        }
+        lane_carry = __shfl_sync(FULL, out, 24 + l);
+        if (has) emit(cx, head + cin, p0 + first_b * CVR_W, s_wb[w][first_b][t], carry_slot);
+        __syncwarp(); // slots are reused by the next tile's delivery
+    }
+
+    // ---- chunk epilogue: lane remainders through the eight pos=-1 records (spmv.cpp:1633-1649)
+    double carry = carry_slot + __shfl_xor_sync(FULL, carry_slot, 8);
+    carry += __shfl_xor_sync(FULL, carry, 16);
+    const int32_t term_wb = (t < CVR_W) ? rec[n_rec + t].y : 0;
+#pragma unroll
+    for (int k = 0; k < CVR_W; k++) {
+        const double r = __shfl_sync(FULL, lane_carry, k);
+        const int32_t wbk = __shfl_sync(FULL, term_wb, k);
+        if (t == wbk) carry += r;
+    }
+    if (t < CVR_W) {
+        const int32_t row = cp->tail[t];
+        if (row != 0) atomicAdd(&y[row], carry); // row 0 = phantom row of unused lanes (carry 0.0)
+    }
+}
+
 } // namespace
 
 int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals,
@@ -198,8 +374,16 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
         return -1;
     const int threads = 128;
     const int blocks = (int)(((int64_t)n_chunks * 32 + threads - 1) / threads);
+    // CVR_SPMV_KERNEL=window selects the first-generation kernel (kept for A/B profiling)
+    static const bool use_window = [] {
+        const char* e = getenv("CVR_SPMV_KERNEL");
+        return e && strcmp(e, "window") == 0;
+    }();
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    cvr_spmv_kernel<<<blocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
+    if (use_window)
+        cvr_spmv_window_kernel<<<blocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
+    else
+        cvr_spmv_kernel<<<blocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
     if (ev_end) cudaEventRecord(ev_end, stream);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return 1;
