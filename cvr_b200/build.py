@@ -59,7 +59,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and _newer(LIB, deps):
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    log = _run([_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, *srcs, "-lgomp"], verbose)
+    extra = os.environ.get("CVR_NVCC_EXTRA", "").split()  # experiments, e.g. -DCVR_MIN_BLOCKS=8
+    log = _run([_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", LIB, *srcs, "-lgomp"], verbose)
     with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
         f.write(log)
     return LIB

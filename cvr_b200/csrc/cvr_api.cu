@@ -290,18 +290,20 @@ int cvr_auto_chunks(int64_t nnz, int device, int32_t* n_chunks)
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
         return fail(CVR_ERR_CUDA, "cannot query device %d: no CPU fallback", device);
-    // One warp per chunk.  Aim at ~2K elements (24 KB of stream) per chunk so the fixed
-    // per-chunk cost (15 records, 9 atomics) stays small, but never fewer chunks than fill
-    // every SM with 32 warps; round to a whole number of SM-wide waves.
+    // One warp per chunk, chunks are nnz-balanced: size the count in whole WAVES of resident
+    // warps (SMs x warps the SpMV kernel keeps resident per SM) so the last wave is full, and
+    // aim at ~2K elements (24 KB of stream) per chunk so the fixed per-chunk cost (15 records,
+    // 9 atomics, descriptor) stays small.
     int64_t target_nnz = 2048;
     if (const char* s = getenv("CVR_CHUNK_NNZ")) {
         const long long v = atoll(s);
         if (v >= 16) target_nnz = v;
     }
-    int64_t t = nnz / target_nnz;
-    const int64_t fill = (int64_t)sms * 32;
-    if (t < fill) t = fill;
-    t = (t + sms - 1) / sms * sms;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(CVR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    const int64_t wave = (int64_t)sms * cvr_spmv_resident_warps_per_sm();
+    int64_t waves = (nnz / target_nnz + wave / 2) / wave;
+    if (waves < 1) waves = 1;
+    int64_t t = waves * wave;
     if (t > nnz / 16) t = nnz / 16;
     if (t > 0x3fffffff) t = 0x3fffffff;
     if (t < 1) t = 1;

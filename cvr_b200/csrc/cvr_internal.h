@@ -64,3 +64,6 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
                     int64_t n_rows, cudaStream_t stream, cudaEvent_t ev_begin = nullptr,
                     cudaEvent_t ev_end = nullptr);
+
+// resident warps per SM of the SpMV kernel in use (sizes the automatic chunk count)
+int cvr_spmv_resident_warps_per_sm();

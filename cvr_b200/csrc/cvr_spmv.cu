@@ -27,6 +27,7 @@
 // stream, inside the timed region).
 #include "cvr_internal.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -199,8 +200,8 @@ cvr_spmv_window_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
 // nnz per row some lane switches rows in 3 of 4 windows, so nearly every window paid the
 // warp-wide segmented reduction (82 warp-instructions per 32 nnz, 43 % issue utilisation,
 // 2.1 TB/s).  Here a warp still owns one chunk, but a pass covers a TILE of 32 steps x 8
-// lanes = 256 elements and thread t = (q, l) walks EIGHT CONSECUTIVE steps of SIMD lane l:
-// steps 8q .. 8q+7 of the tile.  A row switch is then a thread-local event (emit the
+// lanes and thread t = (q, l) walks TB CONSECUTIVE steps of SIMD lane l:
+// steps TB*q .. TB*q+TB-1 of the tile.  A row switch is then a thread-local event (emit the
 // accumulator, clear it); threads of the same SIMD lane only meet once per tile, in a
 // 3-shuffle carry chain that hands the open partial sum from walker q to walker q+1.
 //   * loads: for each of the 8 steps a warp load touches 4 x 64 B (vals) / 4 x 32 B (cols)
@@ -208,11 +209,37 @@ cvr_spmv_window_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
 //   * records are delivered to their owner thread through shared memory: the warp holds 32
 //     records in registers (coalesced 256 B load), each holder drops a flag byte and the
 //     write-back target into the owner's slot.
+//   * kTma = true (default): the vals/cols stream does not go through the LSU at all.  ncu on
+//     the LDG variant (profiles/r01_v1_*) shows the L1TEX data pipe as the busiest unit
+//     (57-74 % of its wavefront peak): every x gather costs one wavefront per distinct line,
+//     so the streamed operands are moved by the TMA engine instead: per tile one lane arms an
+//     mbarrier and eight lanes issue cp.async.bulk (global -> shared, L2 evict-first), two
+//     stages deep, i.e. the copy of tile k+1/k+2 overlaps the gather + FMA walk of tile k.
+//     Each walker's quarter of the tile lands in its own padded slot so that the 64-bit
+//     shared loads of the four walkers fall on disjoint banks.
 // ---------------------------------------------------------------------------------------
-constexpr int TB = 8;                 // consecutive steps per walker
-constexpr int TILE = 4 * TB * CVR_W;  // 256 elements per warp pass
+// TB (consecutive steps per walker) is 9 for the TMA variant, ODD on purpose: a walker's
+// quarter of the tile is then 9 x 64 B = 576 B of vals and 288 B of cols, so the four walkers
+// start 16 (vals) / 8 (cols) shared-memory banks apart and their 64-bit / 32-bit loads of one
+// step are conflict-free in the plain linear layout ONE bulk copy per array produces.  (With
+// TB = 8 the quarters alias on the same banks; padding each quarter separately needed 8 small
+// copies per tile.)  The LDG variant has no such constraint and uses TB = 8.
 constexpr int WARPS = 4;              // warps per block
 constexpr int32_t WB_SPLIT0 = -2;     // marker: flush into the shared first row
+#ifndef CVR_TMA_STAGES
+#define CVR_TMA_STAGES 1
+#endif
+constexpr int STAGES = CVR_TMA_STAGES; // TMA ring depth per warp (1: the registers are the 2nd buffer)
+
+template <int TB>
+struct Geo {
+    static constexpr int TILE = 4 * TB * CVR_W;      // elements per warp pass (TB=9: 288, 36 steps)
+    static constexpr int QUARTER = TB * CVR_W;       // one walker's share of a tile
+    static constexpr int FLAG_WORDS = (TB + 3) / 4;  // flag bytes per thread, packed in 32-bit words
+    static constexpr int STAGE_BYTES = TILE * 12;    // vals then cols
+    static constexpr int WARP_SMEM = STAGES * STAGE_BYTES;
+    static constexpr int DYN_SMEM = WARPS * WARP_SMEM;
+};
 
 struct TileCtx {
     double* __restrict__ y;
@@ -224,144 +251,294 @@ struct TileCtx {
 __device__ __forceinline__ void emit(const TileCtx& cx, double value, int32_t pos, int32_t wb,
                                      double& carry_slot)
 {
-    if (wb == WB_SPLIT0) atomicAdd(&cx.y[cx.first_row], value);            // spmv.cpp:1280-1282
-    else if (cx.split1 != -1 && pos <= cx.split1) cx.y[wb] = value;        // feeding, :1204
+    if (wb >= 0 && pos <= cx.split1) cx.y[wb] = value;                     // feeding, :1204 (split1 = -1: never)
+    else if (wb == WB_SPLIT0) atomicAdd(&cx.y[cx.first_row], value);       // spmv.cpp:1280-1282
     else if (wb == cx.l) carry_slot += value;                              // stealing, :1541
     else if (cx.tail[wb] != 0) atomicAdd(&cx.y[cx.tail[wb]], value);       // (unreachable)
 }
 
-__global__ void __launch_bounds__(WARPS * 32)
-cvr_spmv_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
-                const double* __restrict__ vals, const int32_t* __restrict__ cols,
-                const int32_t* __restrict__ record, const double* __restrict__ x,
-                double* __restrict__ y)
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
-    __shared__ unsigned long long s_flags[WARPS][32]; // 8 flag bytes per thread (one per step)
-    __shared__ int32_t s_wb[WARPS][TB][32];           // write-back target per (step, thread)
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                         uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
 
-    const int32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (chunk >= T) return;
+// flag bytes (0/1) of a 32-bit word -> 4-bit mask
+__device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return ((w * 0x00204081u) >> 21) & 0xfu; }
+
+#ifndef CVR_LDG_BLOCKS
+#define CVR_LDG_BLOCKS 8
+#endif
+#ifndef CVR_TMA_BLOCKS
+#define CVR_TMA_BLOCKS 6
+#endif
+
+template <bool kTma, int TB>
+__global__ void __launch_bounds__(WARPS * 32, kTma ? CVR_TMA_BLOCKS : CVR_LDG_BLOCKS)
+cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
+                     const double* __restrict__ vals, const int32_t* __restrict__ cols,
+                     const int32_t* __restrict__ record, const double* __restrict__ x,
+                     double* __restrict__ y)
+{
+    using G = Geo<TB>;
+    constexpr int TILE = G::TILE, QUARTER = G::QUARTER, FLAG_WORDS = G::FLAG_WORDS;
+    __shared__ uint32_t s_flags[WARPS][FLAG_WORDS][32]; // one flag byte per (thread, step)
+    __shared__ int32_t s_wb[WARPS][TB][32];             // write-back target per (step, thread)
+    __shared__ __align__(8) unsigned long long s_bar[WARPS][STAGES];
+    extern __shared__ __align__(128) unsigned char s_stream[]; // kTma: WARPS x STAGES tiles
+
     const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = t >> 3, l = t & 7;
+    const int32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int32_t n_warps = (gridDim.x * blockDim.x) >> 5;
 
-    const CvrChunk* cp = chunks + chunk;
-    const int64_t start = cp->start;
-    const int32_t len = cp->len;
-    const int32_t split0 = cp->split0;
-    const int32_t n_rec = cp->n_rec;
-    TileCtx cx;
-    cx.y = y;
-    cx.tail = cp->tail;
-    cx.split1 = cp->split1;
-    cx.first_row = cp->first_row;
-    cx.l = l;
-
-    const int2* rec = reinterpret_cast<const int2*>(record + cvr_record_offset(chunk, cx.first_row));
-    const double* v = vals + start;
-    const int32_t* c = cols + start;
-
-    s_flags[w][t] = 0ull;
-    int32_t rb = 0;
-    int2 held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
-    double lane_carry = 0.0; // open partial sum of SIMD lane l at the tile boundary
-    double carry_slot = 0.0; // private share of t_rets[l] (spmv.cpp:1124)
+    // ---- per-warp TMA ring, set up once: the warp is persistent and walks chunks
+    // warp0, warp0 + n_warps, ... (chunks are nnz-balanced, so a static round robin is even)
+    const uint32_t ring = kTma ? smem_u32(s_stream + w * G::WARP_SMEM) : 0u;
+    const uint32_t bar0 = kTma ? smem_u32(&s_bar[w][0]) : 0u;
+    uint64_t policy = 0;
+    uint32_t n_issued = 0, n_waited = 0; // tiles issued to / consumed from the ring, all chunks
+    if (kTma) {
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        if (t == 0) {
+#pragma unroll
+            for (int sidx = 0; sidx < STAGES; sidx++) mbar_init(bar0 + 8u * sidx, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < FLAG_WORDS; k++) s_flags[w][k][t] = 0u;
     __syncwarp();
 
-    const int32_t n_tiles = (len + TILE - 1) / TILE;
-    for (int32_t tile = 0; tile < n_tiles; tile++) {
-        const int32_t ts = tile * TILE;
-        const int32_t p0 = ts + q * (TB * CVR_W) + l; // my element of step 8q; next step: +8
+    for (int32_t chunk = warp0; chunk < T; chunk += n_warps) {
+        const CvrChunk* cp = chunks + chunk;
+        const int64_t start = cp->start;
+        const int32_t len = cp->len;
+        const int32_t split0 = cp->split0;
+        const int32_t n_rec = cp->n_rec;
+        TileCtx cx;
+        cx.y = y;
+        cx.tail = cp->tail;
+        cx.split1 = cp->split1;
+        cx.first_row = cp->first_row;
+        cx.l = l;
 
-        double a[TB], xv[TB];
-        int32_t ci[TB];
-#pragma unroll
-        for (int b = 0; b < TB; b++) {
-            const int32_t p = p0 + b * CVR_W;
-            const bool in = p < len;
-            a[b] = in ? ld_stream_f64(v + p) : 0.0;
-            ci[b] = in ? ld_stream_s32(c + p) : 0;
-        }
-#pragma unroll
-        for (int b = 0; b < TB; b++) xv[b] = __ldg(x + ci[b]);
+        const int2* rec = reinterpret_cast<const int2*>(record + cvr_record_offset(chunk, cx.first_row));
+        const double* v = vals + start;
+        const int32_t* c = cols + start;
+        const int32_t n_tiles = (len + TILE - 1) / TILE;
 
-        // ---- deliver the records of this tile to their owner threads
-        for (;;) {
-            const uint32_t rel = (uint32_t)(held.x - ts);
-            if (rel < (uint32_t)TILE) {
-                const uint32_t step = rel >> 3;
-                const uint32_t owner = (step >> 3) * CVR_W + (rel & 7u);
-                reinterpret_cast<unsigned char*>(&s_flags[w][owner])[step & 7u] = 1;
-                s_wb[w][step & 7u][owner] = held.y;
+        // one elected lane arms the stage's mbarrier and issues both bulk copies of a tile
+        auto issue_tile = [&](int32_t tile) {
+            if (t == 0) {
+                const int32_t ts = tile * TILE;
+                const int32_t n_el = min(TILE, len - ts); // multiple of 16
+                const uint32_t sidx = n_issued % STAGES;
+                const uint32_t bar = bar0 + 8u * sidx;
+                const uint32_t stage = ring + sidx * G::STAGE_BYTES;
+                mbar_expect_tx(bar, (uint32_t)n_el * 12u);
+                bulk_g2s(stage, v + ts, (uint32_t)n_el * 8u, bar, policy);
+                bulk_g2s(stage + TILE * 8, c + ts, (uint32_t)n_el * 4u, bar, policy);
             }
-            const int32_t last = __shfl_sync(FULL, held.x, 31);
-            if ((uint32_t)last >= (uint32_t)(ts + TILE)) break; // batch reaches past the tile (or ended)
-            rb += 32;
-            held = (rb + t < n_rec) ? rec[rb + t] : make_int2(-1, 0);
-        }
-        if (t == 0 && split0 != 0) {
-            const uint32_t rel = (uint32_t)(split0 - ts);
-            if (rel < (uint32_t)TILE) {
-                const uint32_t step = rel >> 3;
-                const uint32_t owner = (step >> 3) * CVR_W + (rel & 7u);
-                reinterpret_cast<unsigned char*>(&s_flags[w][owner])[step & 7u] = 1;
-                s_wb[w][step & 7u][owner] = WB_SPLIT0;
-            }
-        }
-        __syncwarp();
-        const unsigned long long f = s_flags[w][t];
-
-        // ---- walk my eight steps; the first flush waits for the carry of earlier walkers
-        double acc = 0.0, head = 0.0;
-        int first_b = -1;
-        if (f == 0ull) {
+            n_issued++;
+        };
+        if (kTma) {
 #pragma unroll
-            for (int b = 0; b < TB; b++) acc = fma(a[b], xv[b], acc);
-        } else {
-            s_flags[w][t] = 0ull;
+            for (int sidx = 0; sidx < STAGES; sidx++)
+                if (sidx < n_tiles) issue_tile(sidx);
+        }
+
+        int32_t rb = 0;
+        int2 held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
+        double lane_carry = 0.0; // open partial sum of SIMD lane l at the tile boundary
+        double carry_slot = 0.0; // private share of t_rets[l] (spmv.cpp:1124)
+
+        for (int32_t tile = 0; tile < n_tiles; tile++) {
+            const int32_t ts = tile * TILE;
+            const int32_t p0 = ts + q * QUARTER + l; // my element of step TB*q of the tile; next step: +8
+            const bool full = ts + TILE <= len;      // warp-uniform: no bounds checks needed
+
+            double a[TB], xv[TB];
+            uint32_t ci[TB];
+            if (kTma) {
+                const uint32_t sidx = n_waited % STAGES;
+                mbar_wait(bar0 + 8u * sidx, (n_waited / STAGES) & 1u);
+                n_waited++;
+                const unsigned char* stage = s_stream + w * G::WARP_SMEM + sidx * G::STAGE_BYTES;
+                const double* sv = reinterpret_cast<const double*>(stage) + q * QUARTER + l;
+                const uint32_t* sc = reinterpret_cast<const uint32_t*>(stage + TILE * 8) + q * QUARTER + l;
+                if (full) {
+#pragma unroll
+                    for (int b = 0; b < TB; b++) {
+                        a[b] = sv[b * CVR_W];
+                        ci[b] = sc[b * CVR_W];
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < TB; b++) {
+                        const bool in = p0 + b * CVR_W < len;
+                        a[b] = in ? sv[b * CVR_W] : 0.0;
+                        ci[b] = in ? sc[b * CVR_W] : 0u;
+                    }
+                }
+                // The refill below is an async-proxy write to the stage these generic-proxy loads
+                // just read: without the proxy fence the bulk copy can land first (observed on
+                // L2-hot inputs).  Fence in every reader, then converge, then re-arm.
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (tile + STAGES < n_tiles) issue_tile(tile + STAGES);
+            } else {
+                const double* gv = v + p0;
+                const uint32_t* gc = reinterpret_cast<const uint32_t*>(c) + p0;
+                if (full) {
+#pragma unroll
+                    for (int b = 0; b < TB; b++) {
+                        a[b] = ld_stream_f64(gv + b * CVR_W);
+                        ci[b] = (uint32_t)ld_stream_s32(reinterpret_cast<const int32_t*>(gc + b * CVR_W));
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < TB; b++) {
+                        const bool in = p0 + b * CVR_W < len;
+                        a[b] = in ? ld_stream_f64(gv + b * CVR_W) : 0.0;
+                        ci[b] = in ? (uint32_t)ld_stream_s32(reinterpret_cast<const int32_t*>(gc + b * CVR_W)) : 0u;
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < TB; b++) xv[b] = __ldg(x + ci[b]);
+
+            // ---- deliver the records of this tile to their owner threads
+            for (;;) {
+                const uint32_t rel = (uint32_t)(held.x - ts);
+                if (rel < (uint32_t)TILE) {
+                    const uint32_t step = rel >> 3, wq = step / TB, b = step - wq * TB;
+                    const uint32_t owner = wq * CVR_W + (rel & 7u);
+                    reinterpret_cast<unsigned char*>(&s_flags[w][b >> 2][owner])[b & 3u] = 1;
+                    s_wb[w][b][owner] = held.y;
+                }
+                const int32_t last = __shfl_sync(FULL, held.x, 31);
+                if ((uint32_t)last >= (uint32_t)(ts + TILE)) break; // batch reaches past the tile (or ended)
+                rb += 32;
+                held = (rb + t < n_rec) ? rec[rb + t] : make_int2(-1, 0);
+            }
+            if (t == 0 && split0 != 0) {
+                const uint32_t rel = (uint32_t)(split0 - ts);
+                if (rel < (uint32_t)TILE) {
+                    const uint32_t step = rel >> 3, wq = step / TB, b = step - wq * TB;
+                    const uint32_t owner = wq * CVR_W + (rel & 7u);
+                    reinterpret_cast<unsigned char*>(&s_flags[w][b >> 2][owner])[b & 3u] = 1;
+                    s_wb[w][b][owner] = WB_SPLIT0;
+                }
+            }
+            __syncwarp();
+            uint32_t mask = 0; // bit b: my SIMD lane switches rows before step b of my share
+#pragma unroll
+            for (int k = 0; k < FLAG_WORDS; k++) {
+                const uint32_t fw = s_flags[w][k][t];
+                if (fw) s_flags[w][k][t] = 0u;
+                mask |= bytes_to_bits(fw) << (4 * k);
+            }
+
+            // ---- walk my TB steps with two predicated FMA chains: `head` collects the steps before
+            // my first flag (everything if I have none), `tail` the steps from my last flag on.
+            const int b_first = mask ? __ffs(mask) - 1 : TB;
+            const int b_last = mask ? 31 - __clz(mask) : TB;
+            const uint32_t below = (1u << b_first) - 1u;        // steps before the first flag
+            const uint32_t after = ~((1u << b_last) - 1u);      // steps from the last flag on
+            double head = 0.0, tailsum = 0.0;
 #pragma unroll
             for (int b = 0; b < TB; b++) {
-                if ((f >> (8 * b)) & 1ull) {
-                    if (first_b < 0) {
-                        head = acc;
-                        first_b = b;
-                    } else {
+                if ((below >> b) & 1u) head = fma(a[b], xv[b], head);
+                if (mask && ((after >> b) & 1u)) tailsum = fma(a[b], xv[b], tailsum);
+            }
+            // segments strictly between two flags of the same thread (short rows): emit in place
+            if (b_last > b_first) {
+                double acc = 0.0;
+#pragma unroll
+                for (int b = 0; b < TB; b++) {
+                    if (b > b_first && ((mask >> b) & 1u)) {
                         emit(cx, acc, p0 + b * CVR_W, s_wb[w][b][t], carry_slot);
+                        acc = 0.0;
                     }
-                    acc = 0.0;
+                    if (b >= b_first && b < b_last) acc = fma(a[b], xv[b], acc);
                 }
-                acc = fma(a[b], xv[b], acc);
             }
-        }
-        const bool has = first_b >= 0;
-        double cin = (q == 0) ? lane_carry : 0.0;
-        double out = has ? acc : cin + acc;
-#pragma unroll
-        for (int r = 1; r < 4; r++) {
-            const double prev = __shfl_up_sync(FULL, out, CVR_W);
-            if (q == r) {
-                cin = prev;
-                out = has ? acc : cin + acc;
-            }
-        }
-        lane_carry = __shfl_sync(FULL, out, 24 + l);
-        if (has) emit(cx, head + cin, p0 + first_b * CVR_W, s_wb[w][first_b][t], carry_slot);
-        __syncwarp(); // slots are reused by the next tile's delivery
-    }
 
-    // ---- chunk epilogue: lane remainders through the eight pos=-1 records (spmv.cpp:1633-1649)
-    double carry = carry_slot + __shfl_xor_sync(FULL, carry_slot, 8);
-    carry += __shfl_xor_sync(FULL, carry, 16);
-    const int32_t term_wb = (t < CVR_W) ? rec[n_rec + t].y : 0;
+            // ---- carry chain over the four walkers of my SIMD lane
+            const bool has = mask != 0u;
+            double cin = (q == 0) ? lane_carry : 0.0;
+            double out = has ? tailsum : cin + head;
 #pragma unroll
-    for (int k = 0; k < CVR_W; k++) {
-        const double r = __shfl_sync(FULL, lane_carry, k);
-        const int32_t wbk = __shfl_sync(FULL, term_wb, k);
-        if (t == wbk) carry += r;
+            for (int r = 1; r < 4; r++) {
+                const double prev = __shfl_up_sync(FULL, out, CVR_W);
+                if (q == r) {
+                    cin = prev;
+                    out = has ? tailsum : cin + head;
+                }
+            }
+            lane_carry = __shfl_sync(FULL, out, 24 + l);
+            if (has) emit(cx, head + cin, p0 + b_first * CVR_W, s_wb[w][b_first][t], carry_slot);
+            __syncwarp(); // slots are reused by the next tile's delivery
+        }
+
+        // ---- chunk epilogue: lane remainders through the eight pos=-1 records (spmv.cpp:1633-1649)
+        double carry = carry_slot + __shfl_xor_sync(FULL, carry_slot, 8);
+        carry += __shfl_xor_sync(FULL, carry, 16);
+        const int32_t term_wb = (t < CVR_W) ? rec[n_rec + t].y : 0;
+#pragma unroll
+        for (int k = 0; k < CVR_W; k++) {
+            const double r = __shfl_sync(FULL, lane_carry, k);
+            const int32_t wbk = __shfl_sync(FULL, term_wb, k);
+            if (t == wbk) carry += r;
+        }
+        if (t < CVR_W) {
+            const int32_t row = cp->tail[t];
+            if (row != 0) atomicAdd(&y[row], carry); // row 0 = phantom row of unused lanes (carry 0.0)
+        }
     }
-    if (t < CVR_W) {
-        const int32_t row = cp->tail[t];
-        if (row != 0) atomicAdd(&y[row], carry); // row 0 = phantom row of unused lanes (carry 0.0)
-    }
+}
+
+constexpr int TB_TMA = 9, TB_LDG = 8;
+
+enum class SpmvKernel { Tma, Ldg, Window };
+
+SpmvKernel selected_kernel()
+{
+    // CVR_SPMV_KERNEL = tma (default) | ldg | window: the earlier generations stay selectable so
+    // that the choice can be re-measured (profiles/ holds the ncu captures of each)
+    static const SpmvKernel k = [] {
+        const char* e = getenv("CVR_SPMV_KERNEL");
+        if (e && strcmp(e, "window") == 0) return SpmvKernel::Window;
+        if (e && strcmp(e, "ldg") == 0) return SpmvKernel::Ldg;
+        return SpmvKernel::Tma;
+    }();
+    return k;
 }
 
 } // namespace
@@ -372,19 +549,59 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
 {
     if (cudaMemsetAsync(y, 0, sizeof(double) * (size_t)(n_rows + 1), stream) != cudaSuccess)
         return -1;
-    const int threads = 128;
+    const int threads = WARPS * 32;
     const int blocks = (int)(((int64_t)n_chunks * 32 + threads - 1) / threads);
-    // CVR_SPMV_KERNEL=window selects the first-generation kernel (kept for A/B profiling)
-    static const bool use_window = [] {
-        const char* e = getenv("CVR_SPMV_KERNEL");
-        return e && strcmp(e, "window") == 0;
-    }();
+    const SpmvKernel k = selected_kernel();
+    // the tile kernels are persistent: one block per resident slot, warps stride over the chunks
+    static int resident_blocks = 0;
+    if (resident_blocks == 0) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident_blocks = sms * (cvr_spmv_resident_warps_per_sm() / WARPS);
+    }
+    int pblocks = blocks < resident_blocks ? blocks : resident_blocks;
+    static int carve = -2;
+    if (carve == -2) { // experiment knob: shared-memory carveout (percent) for the TMA kernel
+        const char* e = getenv("CVR_TMA_CARVEOUT");
+        carve = e ? atoi(e) : -1;
+        if (carve >= 0) {
+            cudaFuncSetAttribute(cvr_spmv_tile_kernel<true, TB_TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            int dev = 0, sms = 0, nb = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cvr_spmv_tile_kernel<true, TB_TMA>, WARPS * 32, Geo<TB_TMA>::DYN_SMEM);
+            if (k == SpmvKernel::Tma) resident_blocks = sms * nb;
+            fprintf(stderr, "cvr: TMA carveout %d%% -> %d blocks/SM\n", carve, nb);
+        }
+    }
+    pblocks = blocks < resident_blocks ? blocks : resident_blocks;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (use_window)
+    if (k == SpmvKernel::Window)
         cvr_spmv_window_kernel<<<blocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
+    else if (k == SpmvKernel::Ldg)
+        cvr_spmv_tile_kernel<false, TB_LDG><<<pblocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
     else
-        cvr_spmv_kernel<<<blocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
+        cvr_spmv_tile_kernel<true, TB_TMA><<<pblocks, threads, Geo<TB_TMA>::DYN_SMEM, stream>>>(chunks, n_chunks, vals, cols,
+                                                                              record, x, y);
     if (ev_end) cudaEventRecord(ev_end, stream);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return 1;
+}
+
+// resident warps per SM of the selected kernel (used to size the automatic chunk count)
+int cvr_spmv_resident_warps_per_sm()
+{
+    int blocks = 0;
+    const SpmvKernel k = selected_kernel();
+    cudaError_t e;
+    if (k == SpmvKernel::Window)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_window_kernel, WARPS * 32, 0);
+    else if (k == SpmvKernel::Ldg)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<false, TB_LDG>, WARPS * 32, 0);
+    else
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<true, TB_TMA>, WARPS * 32,
+                                                          Geo<TB_TMA>::DYN_SMEM);
+    if (e != cudaSuccess || blocks <= 0) return 32;
+    return blocks * WARPS;
 }
