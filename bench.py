@@ -36,6 +36,11 @@ if ROOT not in sys.path:
 METRIC = "spmv_gflops"
 UNIT = "GFLOP/s"
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE cvr_spmv_kernel launch, from the committed
+# `ncu --set full` captures of this very command (profiles/r01_v3_tma_<workload>_ncu.csv)
+NCU_DRAM_TRAFFIC = {"fem": 338.48e6 + 6.82e6, "rmat24": 4015.77e6 + 84.02e6,
+                    "web": 69.51e6 + 2.26e6, "road": 1097.91e6 + 165.75e6}
+
 
 def measured_peaks():
     try:
@@ -223,32 +228,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     del mine
     torch.cuda.empty_cache()
 
-    n_local = cuts[rank + 1] - cuts[rank]
-    counts = [cuts[g + 1] - cuts[g] for g in range(world)]
-    equal = len(set(counts)) == 1
+    from cvr_b200.dist import RowShardExchange
+    exchange = RowShardExchange(cuts, rank, world, dev)
     stream = torch.cuda.current_stream()
     g = torch.Generator(device=dev).manual_seed(99)
     x = torch.rand(n_cols + 1, generator=g, device=dev, dtype=torch.float64) - 0.5
     x[0] = 0.0
     y = torch.zeros(info["n_rows"] + 1, dtype=torch.float64, device=dev)
-    max_cnt = max(counts)
-    stage = torch.zeros(world * max_cnt, dtype=torch.float64, device=dev) if (iterated and not equal) else None
-
-    def exchange():
-        """y shards -> replicated x: the one collective of the iterated SpMV."""
-        if equal:
-            dist.all_gather_into_tensor(x[1:1 + n_rows_total], y[1:1 + n_local])
-        else:
-            pad = torch.zeros(max_cnt, dtype=torch.float64, device=dev)
-            pad[:n_local] = y[1:1 + n_local]
-            dist.all_gather_into_tensor(stage, pad)
-            for gg in range(world):
-                x[cuts[gg]:cuts[gg + 1]] = stage[gg * max_cnt: gg * max_cnt + counts[gg]]
 
     def step():
         m.spmv_device(x, y, stream.cuda_stream)
         if iterated:
-            exchange()
+            exchange(y, x)  # y shards -> replicated x: the one collective of the iterated SpMV
 
     flush = None
     if info["algorithmic_bytes"] < 256e6:  # would sit in the 126 MB L2: flush between steps
@@ -265,7 +256,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- timed region A: K whole steps
     launches0 = m.info["kernel_launches"]
-    with ClockSampler(local_rank) as clocks:
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    if True:
         if flush is None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
@@ -303,6 +296,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     barrier()
     ksecs, klaunches = m.kernel_timing()
     m.set_kernel_timing(False)
+    clocks.__exit__(None, None, None)
     kernel_s = ksecs / max(klaunches, 1)
     peak, peak_src = measured_peaks()
     achieved = info["algorithmic_bytes"] / kernel_s / 1e9
@@ -335,7 +329,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": e2e_gflops, "unit": UNIT, "h2d_bytes_per_step": 8 * (n_cols + 1),
                     "d2h_bytes_per_step": 8 * (info["n_rows"] + 1), "steps": e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": NCU_DRAM_TRAFFIC.get(args.workload) if world == 1 else None,
+                         "traffic_source": "profiles/r01_v3_tma_%s_ncu.csv" % args.workload
+                         if (world == 1 and args.workload in NCU_DRAM_TRAFFIC) else None,
+                         "peak_source": peak_src,
                          "kernel": "cvr_spmv_kernel", "kernel_us": kernel_s * 1e6,
                          "algorithmic_bytes_per_launch": info["algorithmic_bytes"],
                          "kernel_share_of_step": kernel_s * 1e3 / ms_per_step,
