@@ -208,6 +208,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # rank 0 must print exactly one JSON line on stdout: keep NCCL's version banner out of it
+        os.environ["NCCL_DEBUG"] = os.environ.get("CVR_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     import cvr_b200
@@ -236,7 +238,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     x[0] = 0.0
     y = torch.zeros(info["n_rows"] + 1, dtype=torch.float64, device=dev)
 
+    publisher = None
+    if iterated and args.exchange == "peer":
+        from cvr_b200.dist import PeerPublisher
+        publisher = PeerPublisher(m, cuts, rank, world, local_rank)
+        publisher.set_x(x)
+
     def step():
+        if publisher is not None:
+            publisher.step(y, stream.cuda_stream)  # SpMV kernel publishes rows into every peer's next x
+            return
         m.spmv_device(x, y, stream.cuda_stream)
         if iterated:
             exchange(y, x)  # y shards -> replicated x: the one collective of the iterated SpMV
@@ -292,12 +303,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     for _ in range(args.steps):
         if flush is not None:
             flush.fill_(1)
-        m.spmv_device(x, y, stream.cuda_stream)
+        if publisher is not None:
+            publisher.step(y, stream.cuda_stream)  # the sweep kernel incl. its peer stores
+        else:
+            m.spmv_device(x, y, stream.cuda_stream)
     barrier()
     ksecs, klaunches = m.kernel_timing()
     m.set_kernel_timing(False)
     clocks.__exit__(None, None, None)
     kernel_s = ksecs / max(klaunches, 1)
+    if world > 1 and os.environ.get("CVR_BENCH_DEBUG"):
+        allk = [None] * world
+        dist.all_gather_object(allk, (rank, kernel_s * 1e6, info["n_rows"], info["nnz"], info["n_records"]))
+        if rank == 0:
+            print("per-rank sweep kernel us / rows / nnz / records:", allk, file=sys.stderr)
     peak, peak_src = measured_peaks()
     achieved = info["algorithmic_bytes"] / kernel_s / 1e9
 
@@ -324,7 +343,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "config": {"workload": desc, "n_rows": n_rows_total, "nnz": nnz_true_total,
                        "chunks_per_gpu": info["n_chunks"], "iterated_x_from_y": iterated,
                        "l2": "inputs exceed L2 (no flush)" if flush is None else "L2 flushed between steps (384 MB write, untimed)",
-                       "step": "memset(y) + cvr_spmv_kernel" + (" + NCCL all-gather y->x" if iterated else "")},
+                       "step": "clear accumulated rows + cvr_spmv_kernel" + (
+                           (" (publishes y rows into every peer's x over NVLink) + accumulated-rows publish + flag barrier"
+                            if publisher is not None else " + NCCL all-gather y->x") if iterated else "")},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_gflops, "unit": UNIT, "h2d_bytes_per_step": 8 * (n_cols + 1),
                     "d2h_bytes_per_step": 8 * (info["n_rows"] + 1), "steps": e2e_steps},
@@ -352,6 +373,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                     "sample": f"whole matrix, {10 if big else 50} SpMV iterations on the host cores",
                                     "ms_per_spmv": secs * 1e3, "convert_seconds": conv}
         print(json.dumps(line))
+    if publisher is not None:
+        publisher.close()
     m.close()
     if world > 1:
         dist.destroy_process_group()
@@ -366,6 +389,8 @@ def main():
     ap.add_argument("--workload", default="fem")
     ap.add_argument("--chunks", type=int, default=0, help="CVR chunks per GPU (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: y->x exchange fused into the SpMV kernel over peer memory, or NCCL all-gather")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -35,6 +35,10 @@ class CvrInfo(C.Structure):  # cvr_info_t
                 ("kernel_launches", C.c_int64), ("device_bytes", C.c_int64)]
 
 
+class CvrPublish(C.Structure):  # cvr_publish_t
+    _fields_ = [("n_dst", C.c_int32), ("mode", C.c_int32), ("row_offset", C.c_int64), ("dst", C.c_void_p * 8)]
+
+
 class CvrHostCsr(C.Structure):  # cvr_host_csr_t
     _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int64), ("nnz", C.c_int64),
                 ("nnz_file", C.c_int64), ("val", c_double_p), ("col", c_int32_p),
@@ -57,6 +61,13 @@ SIGNATURES = {
     "cvr_create_from_device": (C.c_int, [C.POINTER(CvrCsr), C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
     "cvr_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, c_double_p]),
     "cvr_spmv_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cvr_spmv_publish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CvrPublish), C.POINTER(C.c_void_p),
+                                  C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]),
+    "cvr_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "cvr_peer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "cvr_peer_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "cvr_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "cvr_peer_barrier": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
     "cvr_export": (C.c_int, [C.c_void_p, C.POINTER(CvrArrays)]),
     "cvr_get_info": (C.c_int, [C.c_void_p, C.POINTER(CvrInfo)]),
     "cvr_device_vectors": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),

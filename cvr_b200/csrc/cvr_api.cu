@@ -53,6 +53,7 @@ struct cvr_handle {
     int32_t* cols = nullptr;
     int32_t* record = nullptr;
     CvrChunk* chunks = nullptr;
+    CvrRowLists rows; // accumulated / never-written rows (what needs clearing before a sweep)
     // device vectors for the host-facing call
     double* x = nullptr;
     double* y = nullptr;
@@ -63,6 +64,7 @@ struct cvr_handle {
     int64_t device_bytes = 0;
     std::vector<CvrChunk> host_chunks; // copy of the descriptors (export / info)
     // optional per-launch timing of the SpMV kernel alone (cvr_set_kernel_timing)
+    unsigned int* done_counter = nullptr; // last-block detection of the publish epilogue
     bool timing = false;
     std::vector<cudaEvent_t> timing_events; // begin/end pairs, `timing_used` of them recorded
     size_t timing_used = 0;
@@ -74,6 +76,9 @@ struct cvr_handle {
         cudaFree(cols);
         cudaFree(record);
         cudaFree(chunks);
+        cudaFree(rows.boundary);
+        cudaFree(rows.empty);
+        cudaFree(done_counter);
         cudaFree(x);
         cudaFree(y);
         if (ev0) cudaEventDestroy(ev0);
@@ -166,6 +171,14 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
             break;
         }
         h->launches += launched;
+        const int listed = cvr_build_row_lists(h->chunks, T, csr->row_delim32, csr->row_delim64, h->n_rows,
+                                               &h->rows, h->stream);
+        if (listed < 0) {
+            rc = fail(CVR_ERR_CUDA, "building the row lists failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        h->launches += listed;
+        h->device_bytes += 4 * ((int64_t)h->rows.n_boundary + h->rows.n_empty + 2);
         if ((e = cudaEventRecord(h->ev1, h->stream)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
         if ((e = cudaEventElapsedTime(&ms, h->ev0, h->ev1)) != cudaSuccess) break;
@@ -322,7 +335,49 @@ int cvr_create_from_device(const cvr_csr_t* csr_dev, int32_t n_chunks, int devic
     return create_common(csr_dev, n_chunks, device, true, out);
 }
 
+static int spmv_device_impl(cvr_handle_t* h, const double* x_dev, double* y_dev, const CvrPublish* pub,
+                            void* cuda_stream, const CvrBarrier* bar = nullptr, bool y_is_clear = false);
+
 int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* cuda_stream)
+{
+    return spmv_device_impl(h, x_dev, y_dev, nullptr, cuda_stream);
+}
+
+int cvr_spmv_publish(cvr_handle_t* h, const double* x_dev, double* y_dev, const cvr_publish_t* pub,
+                     void* const* flag_arrays, int32_t rank, int32_t n_ranks, uint32_t epoch,
+                     int32_t y_is_clear, void* cuda_stream)
+{
+    if (!h || !pub) return fail(CVR_ERR_INVALID, "NULL handle / publish descriptor");
+    if (!flag_arrays || n_ranks < 1 || n_ranks > CVR_MAX_PEERS || rank < 0 || rank >= n_ranks)
+        return fail(CVR_ERR_INVALID, "bad barrier arguments to cvr_spmv_publish");
+    CvrBarrier b{};
+    for (int k = 0; k < n_ranks; k++) {
+        if (!flag_arrays[k]) return fail(CVR_ERR_INVALID, "flag_arrays[%d] is NULL", k);
+        b.flags[k] = static_cast<uint32_t*>(flag_arrays[k]);
+    }
+    b.rank = rank;
+    b.n_ranks = n_ranks;
+    b.epoch = epoch;
+    if (!h->done_counter) {
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->done_counter), sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(h->done_counter, 0, sizeof(unsigned int)));
+    }
+    if (pub->n_dst < 1 || pub->n_dst > CVR_MAX_PEERS)
+        return fail(CVR_ERR_INVALID, "n_dst = %d must be in [1, %d]", pub->n_dst, CVR_MAX_PEERS);
+    CvrPublish p{};
+    p.n_dst = pub->n_dst;
+    p.mode = pub->mode;
+    p.row_offset = pub->row_offset;
+    for (int k = 0; k < pub->n_dst; k++) {
+        if (!pub->dst[k]) return fail(CVR_ERR_INVALID, "dst[%d] is NULL", k);
+        p.dst[k] = pub->dst[k];
+    }
+    return spmv_device_impl(h, x_dev, y_dev, &p, cuda_stream, &b, y_is_clear != 0);
+}
+
+static int spmv_device_impl(cvr_handle_t* h, const double* x_dev, double* y_dev, const CvrPublish* pub,
+                            void* cuda_stream, const CvrBarrier* bar, bool y_is_clear)
 {
     if (!h || !x_dev || !y_dev) return fail(CVR_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -340,8 +395,9 @@ int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* c
         h->timing_used += 2;
     }
     const int launched = cvr_launch_spmv(h->chunks, h->n_chunks, h->vals, h->cols, h->record,
-                                         x_dev, y_dev, h->n_rows,
-                                         static_cast<cudaStream_t>(cuda_stream), eb, ee);
+                                         x_dev, y_dev, h->n_rows, h->rows, pub,
+                                         static_cast<cudaStream_t>(cuda_stream), eb, ee, bar,
+                                         h->done_counter, y_is_clear);
     if (launched < 0)
         return fail(CVR_ERR_CUDA, "SpMV launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += launched;
@@ -453,6 +509,62 @@ int cvr_get_kernel_timing(cvr_handle_t* h, double* total_seconds, int64_t* launc
     *total_seconds = total;
     *launches = (int64_t)(h->timing_used / 2);
     h->timing_used = 0;
+    return CVR_OK;
+}
+
+int cvr_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char handle[64])
+{
+    if (!dev_ptr || !handle || bytes <= 0) return fail(CVR_ERR_INVALID, "bad arguments to cvr_peer_alloc");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(dev_ptr, (size_t)bytes));
+    CUDA_TRY(cudaMemset(*dev_ptr, 0, (size_t)bytes));
+    cudaIpcMemHandle_t hnd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hnd, *dev_ptr));
+    memcpy(handle, &hnd, 64);
+    return CVR_OK;
+}
+
+int cvr_peer_open(int device, const unsigned char handle[64], void** dev_ptr)
+{
+    if (!dev_ptr || !handle) return fail(CVR_ERR_INVALID, "bad arguments to cvr_peer_open");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+    return CVR_OK;
+}
+
+int cvr_peer_close(int device, void* dev_ptr)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return CVR_OK;
+}
+
+int cvr_peer_free(int device, void* dev_ptr)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(dev_ptr));
+    return CVR_OK;
+}
+
+int cvr_peer_barrier(int device, void* const* flag_arrays, int32_t rank, int32_t n_ranks, uint32_t epoch,
+                     void* cuda_stream)
+{
+    if (!flag_arrays || n_ranks < 1 || n_ranks > CVR_MAX_PEERS || rank < 0 || rank >= n_ranks)
+        return fail(CVR_ERR_INVALID, "bad arguments to cvr_peer_barrier");
+    CUDA_TRY(cudaSetDevice(device));
+    CvrBarrier b{};
+    for (int p = 0; p < n_ranks; p++) {
+        if (!flag_arrays[p]) return fail(CVR_ERR_INVALID, "flag_arrays[%d] is NULL", p);
+        b.flags[p] = static_cast<uint32_t*>(flag_arrays[p]);
+    }
+    b.rank = rank;
+    b.n_ranks = n_ranks;
+    b.epoch = epoch;
+    if (cvr_launch_peer_barrier(b, static_cast<cudaStream_t>(cuda_stream)) < 0)
+        return fail(CVR_ERR_CUDA, "barrier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return CVR_OK;
 }
 

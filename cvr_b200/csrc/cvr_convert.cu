@@ -262,7 +262,97 @@ cvr_permute_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
     }
 }
 
+__global__ void cvr_mark_boundary_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
+                                         unsigned char* __restrict__ flags)
+{
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const CvrChunk& c = chunks[t];
+    if (c.split0 != 0) flags[c.first_row] = 1;
+#pragma unroll
+    for (int q = 0; q < CVR_W; q++)
+        if (c.tail[q] != 0) flags[c.tail[q]] = 1;
+}
+
+// pass 0 counts, pass 1 appends (order inside a list is irrelevant)
+template <typename RdT>
+__global__ void cvr_collect_rows_kernel(const RdT* __restrict__ rd, int64_t n_rows,
+                                        const unsigned char* __restrict__ flags,
+                                        int32_t* __restrict__ boundary, int32_t* __restrict__ empty,
+                                        int32_t* __restrict__ counters, int pass)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool is_b = false, is_e = false;
+    if (r <= n_rows) {
+        is_b = r >= 1 && flags[r];
+        is_e = !is_b && (r == 0 || rd[r + 1] == rd[r]);
+    }
+    const unsigned mb = __ballot_sync(FULL, is_b), me = __ballot_sync(FULL, is_e);
+    const int lane = threadIdx.x & 31;
+    int base_b = 0, base_e = 0;
+    if (lane == 0) {
+        if (mb) base_b = atomicAdd(&counters[0], __popc(mb));
+        if (me) base_e = atomicAdd(&counters[1], __popc(me));
+    }
+    if (pass == 1) {
+        base_b = __shfl_sync(FULL, base_b, 0);
+        base_e = __shfl_sync(FULL, base_e, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (is_b) boundary[base_b + __popc(mb & lt)] = (int32_t)r;
+        if (is_e) empty[base_e + __popc(me & lt)] = (int32_t)r;
+    }
+}
+
 } // namespace
+
+int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t* rd32, const int64_t* rd64,
+                        int64_t n_rows, CvrRowLists* out, cudaStream_t stream)
+{
+    unsigned char* flags = nullptr;
+    int32_t* counters = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&flags), (size_t)n_rows + 2) != cudaSuccess) return -1;
+    if (cudaMalloc(reinterpret_cast<void**>(&counters), 2 * sizeof(int32_t)) != cudaSuccess) {
+        cudaFree(flags);
+        return -1;
+    }
+    int launched = 0, rc = 0;
+    const int threads = 256;
+    const int row_blocks = (int)((n_rows + 1 + threads - 1) / threads);
+    do {
+        cudaMemsetAsync(flags, 0, (size_t)n_rows + 2, stream);
+        cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), stream);
+        cvr_mark_boundary_kernel<<<(n_chunks + 127) / 128, 128, 0, stream>>>(chunks, n_chunks, flags);
+        if (rd64)
+            cvr_collect_rows_kernel<int64_t><<<row_blocks, threads, 0, stream>>>(rd64, n_rows, flags, nullptr,
+                                                                                  nullptr, counters, 0);
+        else
+            cvr_collect_rows_kernel<int32_t><<<row_blocks, threads, 0, stream>>>(rd32, n_rows, flags, nullptr,
+                                                                                  nullptr, counters, 0);
+        launched += 2;
+        int32_t h[2] = {0, 0};
+        if (cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+            cudaStreamSynchronize(stream) != cudaSuccess) { rc = -1; break; }
+        out->n_boundary = h[0];
+        out->n_empty = h[1];
+        if (cudaMalloc(reinterpret_cast<void**>(&out->boundary), sizeof(int32_t) * (size_t)(h[0] + 1)) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&out->empty), sizeof(int32_t) * (size_t)(h[1] + 1)) != cudaSuccess) {
+            rc = -1;
+            break;
+        }
+        cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), stream);
+        if (rd64)
+            cvr_collect_rows_kernel<int64_t><<<row_blocks, threads, 0, stream>>>(rd64, n_rows, flags, out->boundary,
+                                                                                  out->empty, counters, 1);
+        else
+            cvr_collect_rows_kernel<int32_t><<<row_blocks, threads, 0, stream>>>(rd32, n_rows, flags, out->boundary,
+                                                                                  out->empty, counters, 1);
+        launched += 1;
+        if (cudaStreamSynchronize(stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = -1;
+    } while (0);
+    cudaFree(flags);
+    cudaFree(counters);
+    return rc < 0 ? rc : launched;
+}
 
 int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream)
 {

@@ -38,6 +38,24 @@ __host__ __device__ inline int64_t cvr_segment_offset(int64_t chunk, int64_t fir
     return CVR_SEG_STRIDE * chunk + first_row;
 }
 
+#define CVR_MAX_PEERS 8
+
+// Where finished y rows are published for the NEXT iteration of an iterated, row-sharded SpMV:
+// the x vectors of this GPU and of its peers (peer-mapped device pointers).  Passed by value.
+struct CvrPublish {
+    int32_t n_dst;                 // 0: do not publish
+    int32_t mode;                  // bit 0: per-row stores at emit instead of the coalesced per-chunk push (A/B)
+                                   // bit 1: do not re-publish 0.0 for the never-written rows
+    int64_t row_offset;            // global row = row_offset + local row
+    double* dst[CVR_MAX_PEERS];
+};
+
+struct CvrBarrier {
+    uint32_t* flags[CVR_MAX_PEERS]; // flags[p]: rank p's flag array (n_ranks words), peer-mapped
+    int32_t rank, n_ranks;
+    uint32_t epoch;
+};
+
 struct CvrConvertArgs {
     // CSR on the device (1-based, n_rows+2 delimiters); one of rd32 / rd64
     const double* csr_val;
@@ -57,13 +75,28 @@ struct CvrConvertArgs {
     int32_t* seg_count;
 };
 
+// Rows that are ACCUMULATED (atomics) rather than stored once: chunk first rows that end while
+// feeding (split0) and the eight tail rows of every chunk; and rows nothing writes: empty rows and
+// the phantom row 0.  Only these need clearing before a SpMV.
+struct CvrRowLists {
+    int32_t* boundary = nullptr; // accumulated rows
+    int32_t* empty = nullptr;    // never-written rows (incl. row 0)
+    int32_t n_boundary = 0, n_empty = 0;
+};
+// builds the lists on `stream` (synchronises); returns kernels launched or <0
+int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t* rd32, const int64_t* rd64,
+                        int64_t n_rows, CvrRowLists* out, cudaStream_t stream);
+
 // Launchers (each returns the number of kernels it launched, or <0 on launch failure)
 int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream);
 // ev_begin / ev_end (optional) bracket the SpMV kernel alone, after y has been cleared
 int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals,
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
-                    int64_t n_rows, cudaStream_t stream, cudaEvent_t ev_begin = nullptr,
-                    cudaEvent_t ev_end = nullptr);
+                    int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
+                    cudaStream_t stream, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr,
+                    const CvrBarrier* barrier = nullptr, unsigned int* done_counter = nullptr,
+                    bool y_is_clear = false);
+int cvr_launch_peer_barrier(const CvrBarrier& b, cudaStream_t stream);
 
 // resident warps per SM of the SpMV kernel in use (sizes the automatic chunk count)
 int cvr_spmv_resident_warps_per_sm();

@@ -226,6 +226,7 @@ cvr_spmv_window_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
 // copies per tile.)  The LDG variant has no such constraint and uses TB = 8.
 constexpr int WARPS = 4;              // warps per block
 constexpr int32_t WB_SPLIT0 = -2;     // marker: flush into the shared first row
+constexpr int32_t PUSH_MAX_ROWS = 1024; // widest row range a warp publishes as one contiguous push
 #ifndef CVR_TMA_STAGES
 #define CVR_TMA_STAGES 1
 #endif
@@ -244,14 +245,58 @@ struct Geo {
 struct TileCtx {
     double* __restrict__ y;
     const int32_t* tail;
+    const CvrPublish* pub; // kernel parameter (constant bank); only read when kPublish
+    bool scatter;          // kPublish: publish row by row at emit (chunks whose row range is too wide)
     int32_t split1, first_row;
     int l;
 };
 
+// A finished row that this chunk owns alone: one plain store (spmv.cpp:1204).
+template <bool kPublish>
+__device__ __forceinline__ void store_row(const TileCtx& cx, int32_t row, double value)
+{
+    cx.y[row] = value;
+    if (kPublish && cx.scatter) { // scattered 8-byte peer stores, row by row
+        const int64_t g = cx.pub->row_offset + row;
+#pragma unroll
+        for (int p = 0; p < CVR_MAX_PEERS; p++)
+            if (p < cx.pub->n_dst) cx.pub->dst[p][g] = value;
+    }
+}
+
+// Iterated multi-GPU SpMV: when a warp has finished a chunk it publishes the chunk's whole row
+// range y[first_row .. last_row] -- contiguous, so the peer-mapped stores are coalesced 256 B
+// warp stores over NVLink -- into the x vector every GPU reads in the NEXT iteration.  The transfer
+// thus runs chunk by chunk inside the SpMV kernel, overlapped with the other warps' sweeps.  Rows of
+// the range that are still being accumulated (shared first/last rows, tail rows) are sent as they
+// are and overwritten by cvr_publish_rows_kernel once the sweep is complete (same source GPU, same
+// address, stream order); empty rows carry the 0.0 the clearing kernel put there.
+__device__ __forceinline__ void publish_chunk_rows(const TileCtx& cx, int32_t first_row, int32_t last_row,
+                                                   int t)
+{
+    __threadfence_block(); // this warp's own row stores (made by other lanes) before the re-read
+    __syncwarp();
+    const CvrPublish& pub = *cx.pub;
+    for (int32_t r0 = first_row + t; r0 <= last_row; r0 += 4 * 32) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = (r0 + 32 * u <= last_row) ? __ldcg(cx.y + r0 + 32 * u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (r0 + 32 * u > last_row) break;
+            const int64_t g = pub.row_offset + r0 + 32 * u;
+#pragma unroll
+            for (int p = 0; p < CVR_MAX_PEERS; p++)
+                if (p < pub.n_dst) pub.dst[p][g] = v[u];
+        }
+    }
+}
+
+template <bool kPublish>
 __device__ __forceinline__ void emit(const TileCtx& cx, double value, int32_t pos, int32_t wb,
                                      double& carry_slot)
 {
-    if (wb >= 0 && pos <= cx.split1) cx.y[wb] = value;                     // feeding, :1204 (split1 = -1: never)
+    if (wb >= 0 && pos <= cx.split1) store_row<kPublish>(cx, wb, value);   // feeding, :1204 (split1 = -1: never)
     else if (wb == WB_SPLIT0) atomicAdd(&cx.y[cx.first_row], value);       // spmv.cpp:1280-1282
     else if (wb == cx.l) carry_slot += value;                              // stealing, :1541
     else if (cx.tail[wb] != 0) atomicAdd(&cx.y[cx.tail[wb]], value);       // (unreachable)
@@ -298,12 +343,12 @@ __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return ((w * 0x0
 #define CVR_TMA_BLOCKS 6
 #endif
 
-template <bool kTma, int TB>
+template <bool kTma, int TB, bool kPublish>
 __global__ void __launch_bounds__(WARPS * 32, kTma ? CVR_TMA_BLOCKS : CVR_LDG_BLOCKS)
 cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
                      const double* __restrict__ vals, const int32_t* __restrict__ cols,
                      const int32_t* __restrict__ record, const double* __restrict__ x,
-                     double* __restrict__ y)
+                     double* __restrict__ y, const __grid_constant__ CvrPublish pub)
 {
     using G = Geo<TB>;
     constexpr int TILE = G::TILE, QUARTER = G::QUARTER, FLAG_WORDS = G::FLAG_WORDS;
@@ -344,6 +389,12 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
         TileCtx cx;
         cx.y = y;
         cx.tail = cp->tail;
+        cx.pub = &pub;
+        // A chunk in a very sparse region can span 10^5 (mostly empty) rows: pushing that range from
+        // one warp would serialise; such chunks publish their few finished rows one by one instead
+        // (their empty rows get their 0.0 from cvr_publish_rows_kernel either way).
+        const int32_t chunk_last_row = cp->last_row;
+        cx.scatter = kPublish && ((pub.mode & 1) || chunk_last_row - cp->first_row >= PUSH_MAX_ROWS);
         cx.split1 = cp->split1;
         cx.first_row = cp->first_row;
         cx.l = l;
@@ -483,7 +534,7 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
 #pragma unroll
                 for (int b = 0; b < TB; b++) {
                     if (b > b_first && ((mask >> b) & 1u)) {
-                        emit(cx, acc, p0 + b * CVR_W, s_wb[w][b][t], carry_slot);
+                        emit<kPublish>(cx, acc, p0 + b * CVR_W, s_wb[w][b][t], carry_slot);
                         acc = 0.0;
                     }
                     if (b >= b_first && b < b_last) acc = fma(a[b], xv[b], acc);
@@ -503,7 +554,7 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
                 }
             }
             lane_carry = __shfl_sync(FULL, out, 24 + l);
-            if (has) emit(cx, head + cin, p0 + b_first * CVR_W, s_wb[w][b_first][t], carry_slot);
+            if (has) emit<kPublish>(cx, head + cin, p0 + b_first * CVR_W, s_wb[w][b_first][t], carry_slot);
             __syncwarp(); // slots are reused by the next tile's delivery
         }
 
@@ -521,10 +572,90 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
             const int32_t row = cp->tail[t];
             if (row != 0) atomicAdd(&y[row], carry); // row 0 = phantom row of unused lanes (carry 0.0)
         }
+        if (kPublish && !cx.scatter) publish_chunk_rows(cx, cx.first_row, chunk_last_row, t);
     }
 }
 
 constexpr int TB_TMA = 9, TB_LDG = 8;
+
+// ---- small helper kernels around the sweep
+// y is cleared only where it is accumulated (boundary rows) or never written (empty rows, row 0):
+// every other row is stored exactly once by the sweep.  Replaces an 8*(nRows+1)-byte memset.
+__global__ void cvr_clear_rows_kernel(double* __restrict__ y, const int32_t* __restrict__ boundary,
+                                      int32_t n_boundary, const int32_t* __restrict__ empty, int32_t n_empty)
+{
+    const int32_t n = n_boundary + n_empty;
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        y[i < n_boundary ? boundary[i] : empty[i - n_boundary]] = 0.0;
+}
+
+// After the sweep of an iterated multi-GPU SpMV, ONE epilogue kernel does everything that has to
+// wait for the sweep to be complete:
+//   1. the accumulated rows are final now: publish them; rows nothing writes get an explicit 0.0
+//      (only while `publish_empty`: a reused x buffer must not keep a stale value there -- two
+//      iterations cover both buffers);
+//   2. clear those rows of y again, ready for the next sweep (cvr_launch_spmv then skips its own
+//      clearing kernel);
+//   3. the last block to finish runs the all-to-all flag barrier over peer memory.
+__global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_t* __restrict__ boundary,
+                                            int32_t n_boundary, const int32_t* __restrict__ empty,
+                                            int32_t n_empty, const __grid_constant__ CvrPublish pub,
+                                            const __grid_constant__ CvrBarrier bar, unsigned int* done_counter)
+{
+    const bool publish_empty = (pub.mode & 2) == 0;
+    const int32_t n = n_boundary + (publish_empty ? n_empty : 0);
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const bool b = i < n_boundary;
+        const int32_t row = b ? boundary[i] : empty[i - n_boundary];
+        if (row == 0) continue; // the phantom row has no global counterpart
+        double v = 0.0;
+        if (b) {
+            v = y[row];
+            y[row] = 0.0;
+        }
+        const int64_t g = pub.row_offset + row;
+#pragma unroll
+        for (int p = 0; p < CVR_MAX_PEERS; p++)
+            if (p < pub.n_dst) pub.dst[p][g] = v;
+    }
+    // ---- last block: flag barrier (see cvr_peer_barrier_kernel)
+    __shared__ bool is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    if (threadIdx.x == 0) *done_counter = 0u;
+    const int p = threadIdx.x;
+    if (p >= bar.n_ranks) return;
+    __threadfence_system();
+    volatile uint32_t* remote = bar.flags[p] + bar.rank;
+    *remote = bar.epoch;
+    volatile uint32_t* mine = bar.flags[bar.rank] + p;
+    const long long t0 = clock64();
+    while ((int32_t)(*mine - bar.epoch) < 0) {
+        if (clock64() - t0 > 6000000000LL) break; // ~3 s: a lost peer must not hang the GPU
+    }
+    __threadfence_system();
+}
+
+// All-to-all flag barrier over peer-mapped memory: every rank writes `epoch` into its slot of every
+// rank's flag array (after a system-scope fence, so the rows it published are visible first) and
+// waits until all of its own slots carry the epoch.  Bounded spin: a lost peer must not hang the GPU.
+__global__ void cvr_peer_barrier_kernel(const __grid_constant__ CvrBarrier b)
+{
+    const int p = threadIdx.x;
+    if (p >= b.n_ranks) return;
+    __threadfence_system();
+    volatile uint32_t* remote = b.flags[p] + b.rank;
+    *remote = b.epoch;
+    volatile uint32_t* mine = b.flags[b.rank] + p;
+    const long long t0 = clock64();
+    while ((int32_t)(*mine - b.epoch) < 0) {
+        if (clock64() - t0 > 6000000000LL) break; // ~3 s
+    }
+    __threadfence_system();
+}
 
 enum class SpmvKernel { Tma, Ldg, Window };
 
@@ -543,52 +674,6 @@ SpmvKernel selected_kernel()
 
 } // namespace
 
-int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals,
-                    const int32_t* cols, const int32_t* record, const double* x, double* y,
-                    int64_t n_rows, cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end)
-{
-    if (cudaMemsetAsync(y, 0, sizeof(double) * (size_t)(n_rows + 1), stream) != cudaSuccess)
-        return -1;
-    const int threads = WARPS * 32;
-    const int blocks = (int)(((int64_t)n_chunks * 32 + threads - 1) / threads);
-    const SpmvKernel k = selected_kernel();
-    // the tile kernels are persistent: one block per resident slot, warps stride over the chunks
-    static int resident_blocks = 0;
-    if (resident_blocks == 0) {
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        resident_blocks = sms * (cvr_spmv_resident_warps_per_sm() / WARPS);
-    }
-    int pblocks = blocks < resident_blocks ? blocks : resident_blocks;
-    static int carve = -2;
-    if (carve == -2) { // experiment knob: shared-memory carveout (percent) for the TMA kernel
-        const char* e = getenv("CVR_TMA_CARVEOUT");
-        carve = e ? atoi(e) : -1;
-        if (carve >= 0) {
-            cudaFuncSetAttribute(cvr_spmv_tile_kernel<true, TB_TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            int dev = 0, sms = 0, nb = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cvr_spmv_tile_kernel<true, TB_TMA>, WARPS * 32, Geo<TB_TMA>::DYN_SMEM);
-            if (k == SpmvKernel::Tma) resident_blocks = sms * nb;
-            fprintf(stderr, "cvr: TMA carveout %d%% -> %d blocks/SM\n", carve, nb);
-        }
-    }
-    pblocks = blocks < resident_blocks ? blocks : resident_blocks;
-    if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (k == SpmvKernel::Window)
-        cvr_spmv_window_kernel<<<blocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
-    else if (k == SpmvKernel::Ldg)
-        cvr_spmv_tile_kernel<false, TB_LDG><<<pblocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
-    else
-        cvr_spmv_tile_kernel<true, TB_TMA><<<pblocks, threads, Geo<TB_TMA>::DYN_SMEM, stream>>>(chunks, n_chunks, vals, cols,
-                                                                              record, x, y);
-    if (ev_end) cudaEventRecord(ev_end, stream);
-    if (cudaGetLastError() != cudaSuccess) return -1;
-    return 1;
-}
-
 // resident warps per SM of the selected kernel (used to size the automatic chunk count)
 int cvr_spmv_resident_warps_per_sm()
 {
@@ -598,10 +683,81 @@ int cvr_spmv_resident_warps_per_sm()
     if (k == SpmvKernel::Window)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_window_kernel, WARPS * 32, 0);
     else if (k == SpmvKernel::Ldg)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<false, TB_LDG>, WARPS * 32, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<false, TB_LDG, false>,
+                                                          WARPS * 32, 0);
     else
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<true, TB_TMA>, WARPS * 32,
-                                                          Geo<TB_TMA>::DYN_SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<true, TB_TMA, false>,
+                                                          WARPS * 32, Geo<TB_TMA>::DYN_SMEM);
     if (e != cudaSuccess || blocks <= 0) return 32;
     return blocks * WARPS;
+}
+
+int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals,
+                    const int32_t* cols, const int32_t* record, const double* x, double* y,
+                    int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
+                    cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end,
+                    const CvrBarrier* barrier, unsigned int* done_counter, bool y_is_clear)
+{
+    int launched = 0;
+    const SpmvKernel k = selected_kernel();
+    const int32_t n_clear = rows.n_boundary + rows.n_empty;
+    if (y_is_clear) {
+        // the previous iteration's epilogue kernel already cleared the accumulated rows
+    } else if (rows.boundary && k != SpmvKernel::Window) {
+        const int cb = (n_clear + 255) / 256;
+        cvr_clear_rows_kernel<<<cb < 1184 ? (cb < 1 ? 1 : cb) : 1184, 256, 0, stream>>>(
+            y, rows.boundary, rows.n_boundary, rows.empty, rows.n_empty);
+        launched++;
+    } else if (cudaMemsetAsync(y, 0, sizeof(double) * (size_t)(n_rows + 1), stream) != cudaSuccess) {
+        return -1;
+    }
+    const int threads = WARPS * 32;
+    const int blocks = (int)(((int64_t)n_chunks * 32 + threads - 1) / threads);
+    // the tile kernels are persistent: one block per resident slot, warps stride over the chunks
+    static int resident_blocks = 0;
+    if (resident_blocks == 0) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident_blocks = sms * (cvr_spmv_resident_warps_per_sm() / WARPS);
+    }
+    const int pblocks = blocks < resident_blocks ? blocks : resident_blocks;
+    CvrPublish none{};
+    const bool pub = publish && publish->n_dst > 0;
+    if (pub && k == SpmvKernel::Window) return -1;
+    if (ev_begin) cudaEventRecord(ev_begin, stream);
+    if (k == SpmvKernel::Window)
+        cvr_spmv_window_kernel<<<blocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
+    else if (k == SpmvKernel::Ldg) {
+        if (pub)
+            cvr_spmv_tile_kernel<false, TB_LDG, true><<<pblocks, threads, 0, stream>>>(
+                chunks, n_chunks, vals, cols, record, x, y, *publish);
+        else
+            cvr_spmv_tile_kernel<false, TB_LDG, false><<<pblocks, threads, 0, stream>>>(
+                chunks, n_chunks, vals, cols, record, x, y, none);
+    } else {
+        if (pub)
+            cvr_spmv_tile_kernel<true, TB_TMA, true><<<pblocks, threads, Geo<TB_TMA>::DYN_SMEM, stream>>>(
+                chunks, n_chunks, vals, cols, record, x, y, *publish);
+        else
+            cvr_spmv_tile_kernel<true, TB_TMA, false><<<pblocks, threads, Geo<TB_TMA>::DYN_SMEM, stream>>>(
+                chunks, n_chunks, vals, cols, record, x, y, none);
+    }
+    launched++;
+    if (ev_end) cudaEventRecord(ev_end, stream);
+    if (pub) {
+        if (!barrier || !done_counter) return -1;
+        const int cb = (n_clear + 255) / 256;
+        cvr_publish_epilogue_kernel<<<cb < 592 ? (cb < 1 ? 1 : cb) : 592, 256, 0, stream>>>(
+            y, rows.boundary, rows.n_boundary, rows.empty, rows.n_empty, *publish, *barrier, done_counter);
+        launched++;
+    }
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return launched;
+}
+
+int cvr_launch_peer_barrier(const CvrBarrier& b, cudaStream_t stream)
+{
+    cvr_peer_barrier_kernel<<<1, 32, 0, stream>>>(b);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

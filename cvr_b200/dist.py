@@ -12,6 +12,8 @@ local SpMV is whatever callable the caller passes (CvrMatrix.spmv_device on GPUs
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -56,3 +58,121 @@ def iterate(local_spmv, exchange: RowShardExchange, x: torch.Tensor, y_local: to
     for _ in range(iters):
         local_spmv(x, y_local)
         exchange(y_local, x)
+
+
+class PeerPublisher:
+    """Fused exchange for the iterated, row-sharded SpMV: instead of an all-gather after the
+    kernel, every finished y row is stored by the SpMV kernel itself into the x vector that each
+    GPU reads in the NEXT iteration (own buffer + peer-mapped buffers over NVLink/NVSwitch), the
+    few accumulated rows follow from a tiny kernel, and iterations are separated by a flag
+    barrier over peer memory.  x is double-buffered: iteration k reads X[k % 2] and publishes
+    into X[(k + 1) % 2] everywhere.  One process per GPU; torch.distributed only carries the
+    64-byte IPC handles at set-up time.
+    """
+
+    def __init__(self, matrix, cuts, rank: int, world: int, device_index: int, group=None):
+        import ctypes as C
+        from . import _lib
+        if world > 8:
+            raise ValueError("at most 8 peers (CVR_MAX_PEERS)")
+        self.m, self.rank, self.world, self.dev = matrix, rank, world, device_index
+        self.cuts = [int(c) for c in cuts]
+        self.n_rows = self.cuts[-1] - 1
+        self.n_local = self.cuts[rank + 1] - self.cuts[rank]
+        self._lib = _lib.load()
+        self._C, self._libmod = C, _lib
+        nbytes = 8 * (self.n_rows + 1)
+
+        def alloc(n):
+            ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+            _lib.check(self._lib.cvr_peer_alloc(device_index, n, C.byref(ptr), handle))
+            return ptr.value, handle.raw
+
+        self._own = []      # (ptr, handle) of X[0], X[1], flags
+        for n in (nbytes, nbytes, 4 * 64):
+            self._own.append(alloc(n))
+        handles = [None] * world
+        dist.all_gather_object(handles, [h for _, h in self._own], group=group)
+        self._opened = []
+        self.ptrs = []      # ptrs[r] = [X0, X1, flags] of rank r as seen from this process
+        for r in range(world):
+            if r == rank:
+                self.ptrs.append([p for p, _ in self._own])
+                continue
+            row = []
+            for h in handles[r]:
+                ptr = C.c_void_p()
+                _lib.check(self._lib.cvr_peer_open(device_index, h, C.byref(ptr)))
+                row.append(ptr.value)
+                self._opened.append(ptr.value)
+            self.ptrs.append(row)
+        self.pub = []
+        for parity in (0, 1):
+            p = _lib.CvrPublish()
+            p.n_dst = world
+            p.mode = int(os.environ.get("CVR_PUBLISH_MODE", "0"))
+            p.row_offset = self.cuts[rank] - 1
+            for r in range(world):
+                p.dst[r] = self.ptrs[r][parity]
+            self.pub.append(p)
+        self._flags = (C.c_void_p * world)(*[self.ptrs[r][2] for r in range(world)])
+        self.epoch = 0
+        self.k = 0  # iterations done: X[k % 2] holds the current x
+        self._reset_k = 0
+        self._last_y = None
+        dist.barrier(group=group)
+
+    def x_tensor(self, parity=None):
+        """The local x buffer of the given parity (default: the one the next iteration reads) as a
+        torch tensor view (n_rows + 1 doubles)."""
+        from .matrix import _ptr  # noqa: F401
+        parity = self.k % 2 if parity is None else parity
+        return _as_tensor(self.ptrs[self.rank][parity], self.n_rows + 1, self.dev)
+
+    def set_x(self, x: torch.Tensor) -> None:
+        self._reset_k = self.k
+        for p in self.pub:
+            p.mode &= ~2
+        self.x_tensor().copy_(x)
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()
+
+    def step(self, y_local: torch.Tensor, stream: int) -> None:
+        """One iteration x <- A x.  y_local must be the same buffer in consecutive calls (the epilogue
+        kernel leaves its accumulated rows cleared for the next sweep)."""
+        cur, nxt = self.k % 2, (self.k + 1) % 2
+        pub = self.pub[nxt]
+        if self.k == self._reset_k + 2:  # both x buffers now hold 0.0 at the never-written rows
+            for p in self.pub:
+                p.mode |= 2
+        self.epoch += 1
+        same_y = self._last_y == y_local.data_ptr()
+        self.m.spmv_publish(self.ptrs[self.rank][cur], y_local, pub, self._flags, self.rank, self.world,
+                            self.epoch, same_y, stream)
+        self._last_y = y_local.data_ptr()
+        self.k += 1
+
+    def bytes_sent_per_iteration(self) -> int:
+        return 8 * self.n_local * (self.world - 1)
+
+    def close(self) -> None:
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()
+        for p in self._opened:
+            self._lib.cvr_peer_close(self.dev, p)
+        self._opened = []
+        dist.barrier()
+        for p, _ in self._own:
+            self._lib.cvr_peer_free(self.dev, p)
+        self._own = []
+
+
+class _RawCudaArray:
+    """Minimal __cuda_array_interface__ wrapper so torch can view library-owned device memory."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def _as_tensor(ptr: int, n: int, device_index: int) -> torch.Tensor:
+    return torch.as_tensor(_RawCudaArray(ptr, n), device=torch.device("cuda", device_index))

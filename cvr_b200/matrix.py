@@ -133,6 +133,13 @@ class CvrMatrix:
         """Enqueue one SpMV on device vectors (torch tensors or raw pointers) on `stream`."""
         _lib.check(self._lib.cvr_spmv_device(self._h, _ptr(x_dev), _ptr(y_dev), int(stream)))
 
+    def spmv_publish(self, x_dev, y_dev, pub, flag_arrays, rank, n_ranks, epoch, y_is_clear, stream: int = 0) -> None:
+        """One iteration of the row-sharded iterated SpMV: the sweep publishes finished rows into the
+        next iteration's x vectors (own + peer-mapped), an epilogue kernel publishes the accumulated
+        rows and runs the flag barrier.  See cvr_b200.dist.PeerPublisher."""
+        _lib.check(self._lib.cvr_spmv_publish(self._h, _ptr(x_dev), _ptr(y_dev), C.byref(pub), flag_arrays,
+                                              int(rank), int(n_ranks), int(epoch), int(y_is_clear), int(stream)))
+
     # -- measurement aid
     def set_kernel_timing(self, enabled: bool) -> None:
         _lib.check(self._lib.cvr_set_kernel_timing(self._h, int(enabled)))

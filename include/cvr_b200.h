@@ -141,6 +141,40 @@ int cvr_spmv(cvr_handle_t* h, const double* x_host, double* y_host, int32_t iter
  * default stream) without synchronising: y_dev[0..n_rows] = A * x_dev. */
 int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* cuda_stream);
 
+/* ---- iterated SpMV on row shards (multi-GPU; no counterpart in the reference) ----
+ * The matrix is row-sharded by nnz, every GPU holds a replicated x.  cvr_spmv_publish is
+ * cvr_spmv_device plus the exchange: each finished y row is also stored into dst[0..n_dst-1][
+ * row_offset + row], the x vectors (own and peer-mapped) that the NEXT iteration reads, from
+ * inside the SpMV kernel (accumulated rows follow from a small kernel right after it).  One
+ * process per GPU: allocate the x buffers and a flag array with cvr_peer_alloc, exchange the 64-byte
+ * handles through any channel (e.g. torch.distributed), map the peers' with cvr_peer_open, and
+ * separate iterations with cvr_peer_barrier (double-buffer x: iteration k reads buffer k%2 and
+ * publishes into buffer (k+1)%2). */
+#define CVR_MAX_PEERS 8
+typedef struct cvr_publish {
+    int32_t n_dst;       /* 1..CVR_MAX_PEERS destinations, own buffer included */
+    int32_t mode;        /* bit 0: per-row stores instead of the coalesced per-chunk push (A/B);
+                            bit 1: skip the 0.0 for never-written rows (set from the 3rd iteration on) */
+    int64_t row_offset;  /* global row id = row_offset + local row (first cut - 1) */
+    double* dst[CVR_MAX_PEERS];
+} cvr_publish_t;
+/* One iteration = at most three kernels on cuda_stream: [clear the accumulated rows of y, unless
+ * y_is_clear] + the SpMV sweep that pushes finished rows to every dst + one epilogue kernel
+ * (publishes the accumulated rows, clears them in y again for the next sweep -- so pass
+ * y_is_clear = 1 from the second iteration on, as long as y_dev is not touched in between --
+ * and runs the all-to-all flag barrier: flag_arrays / rank / n_ranks / epoch as cvr_peer_barrier). */
+int cvr_spmv_publish(cvr_handle_t* h, const double* x_dev, double* y_dev, const cvr_publish_t* pub,
+                     void* const* flag_arrays, int32_t rank, int32_t n_ranks, uint32_t epoch,
+                     int32_t y_is_clear, void* cuda_stream);
+int cvr_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char handle[64]); /* zero-filled */
+int cvr_peer_open(int device, const unsigned char handle[64], void** dev_ptr);
+int cvr_peer_close(int device, void* dev_ptr);
+int cvr_peer_free(int device, void* dev_ptr);
+/* flag_arrays[p] = rank p's flag array (n_ranks uint32, from cvr_peer_alloc / cvr_peer_open);
+ * epoch must increase by one per call.  Enqueued on cuda_stream. */
+int cvr_peer_barrier(int device, void* const* flag_arrays, int32_t rank, int32_t n_ranks, uint32_t epoch,
+                     void* cuda_stream);
+
 /* Bit-exact gate: copy the CVR structure arrays back in the reference layout. */
 int cvr_export(cvr_handle_t* h, cvr_arrays_t* host_out);
 

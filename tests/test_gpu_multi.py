@@ -23,7 +23,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, iters, out):
+def _worker(rank, world, port, iters, out, fused=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -42,7 +42,17 @@ def _worker(rank, world, port, iters, out):
     x[0] = 0.0
     y = torch.zeros(mine.n_rows + 1, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    iterate(lambda xx, yy: m.spmv_device(xx, yy, stream), ex, x, y, iters)
+    if fused:
+        from cvr_b200.dist import PeerPublisher
+        pp = PeerPublisher(m, cuts, rank, world, rank)
+        pp.set_x(x)
+        for _ in range(iters):
+            pp.step(y, stream)
+        torch.cuda.synchronize()
+        x = pp.x_tensor().clone()
+        pp.close()
+    else:
+        iterate(lambda xx, yy: m.spmv_device(xx, yy, stream), ex, x, y, iters)
     torch.cuda.synchronize()
     if rank == 0:
         torch.save(x.cpu(), out)
@@ -51,13 +61,14 @@ def _worker(rank, world, port, iters, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_iterated_spmv_matches_oracle(tmp_path, native_lib):
+@pytest.mark.parametrize("fused", [False, True], ids=["nccl_allgather", "peer_publish"])
+def test_two_gpu_iterated_spmv_matches_oracle(tmp_path, native_lib, fused):
     import oracle
     from cvr_b200 import gen
     from helpers import to_oracle_csr
     iters = 3
     out = str(tmp_path / "x.pt")
-    mp.spawn(_worker, args=(2, _free_port(), iters, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), iters, out, fused), nprocs=2, join=True)
     got = torch.load(out).numpy()
     full = gen.rmat(14, 16, device="cuda:0", seed=71, row_normalise=True)
     csr = to_oracle_csr(full)
