@@ -216,12 +216,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     from cvr_b200 import shard
 
     iterated = world > 1
-    full, desc, scaling = make_workload(args.workload, world, dev, row_normalise=True)
-    nnz_true_total = full.nnz_true
-    n_rows_total, n_cols = full.n_rows, full.n_cols
-    cuts = shard.partition_rows_by_nnz_torch(full.row_delim, world) if world > 1 else [1, n_rows_total + 1]
-    mine = shard.shard_device_csr(full, cuts[rank], cuts[rank + 1]) if world > 1 else full
-    keep_host = full.to_host() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    big_rmat = None
+    if args.workload == "rmat28":
+        big_rmat = 28
+    elif args.workload.startswith("rmat:") and int(args.workload.split(":")[1]) >= 26:
+        big_rmat = int(args.workload.split(":")[1])
+    if big_rmat is not None:
+        # config 5: too large to build on one GPU -- every rank generates only its own row shard
+        from cvr_b200 import gen
+        mine, cuts, nt = gen.rmat_shard(big_rmat, 16, rank, world, dev, row_normalise=True)
+        tot = torch.tensor([nt], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        nnz_true_total = int(tot.item())
+        n_rows_total = n_cols = 1 << big_rmat
+        desc = f"R-MAT scale {big_rmat} edge factor 16, generated per row shard (BASELINE configs[4] at scale 28)"
+        scaling = "strong"
+        full = None
+    else:
+        full, desc, scaling = make_workload(args.workload, world, dev, row_normalise=True)
+        nnz_true_total = full.nnz_true
+        n_rows_total, n_cols = full.n_rows, full.n_cols
+        cuts = shard.partition_rows_by_nnz_torch(full.row_delim, world) if world > 1 else [1, n_rows_total + 1]
+        mine = shard.shard_device_csr(full, cuts[rank], cuts[rank + 1]) if world > 1 else full
+    keep_host = full.to_host() if (full is not None and rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     del full
     torch.cuda.synchronize()
 
@@ -241,7 +259,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     publisher = None
     if iterated and args.exchange == "peer":
         from cvr_b200.dist import PeerPublisher
-        publisher = PeerPublisher(m, cuts, rank, world, local_rank)
+        publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange)
         publisher.set_x(x)
 
     def step():
@@ -362,6 +380,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "clocks": clocks.summary(),
             "extra": {"step_gbs": info["algorithmic_bytes"] * world / (ms_per_step * 1e-3) / 1e9 if scaling == "weak"
                       else None,
+                      "peer_bytes_sent_per_step_rank0": publisher.bytes_sent_per_iteration() if publisher else None,
                       "convert_seconds_device": info["convert_seconds"],
                       "create_seconds": info["create_seconds"], "n_records": info["n_records"]},
         }
@@ -389,6 +408,8 @@ def main():
     ap.add_argument("--workload", default="fem")
     ap.add_argument("--chunks", type=int, default=0, help="CVR chunks per GPU (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-exchange", action="store_true",
+                    help="peer exchange: publish every row to every GPU instead of only to the GPUs that read it")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: y->x exchange fused into the SpMV kernel over peer memory, or NCCL all-gather")
     args = ap.parse_args()

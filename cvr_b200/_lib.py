@@ -36,7 +36,8 @@ class CvrInfo(C.Structure):  # cvr_info_t
 
 
 class CvrPublish(C.Structure):  # cvr_publish_t
-    _fields_ = [("n_dst", C.c_int32), ("mode", C.c_int32), ("row_offset", C.c_int64), ("dst", C.c_void_p * 8)]
+    _fields_ = [("n_dst", C.c_int32), ("mode", C.c_int32), ("row_offset", C.c_int64), ("needs", C.c_void_p),
+                ("chunk_any", C.c_void_p), ("clear_next", C.c_void_p), ("dst", C.c_void_p * 8)]
 
 
 class CvrHostCsr(C.Structure):  # cvr_host_csr_t
@@ -63,6 +64,8 @@ SIGNATURES = {
     "cvr_spmv_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvr_spmv_publish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CvrPublish), C.POINTER(C.c_void_p),
                                   C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]),
+    "cvr_column_footprint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cvr_chunk_needs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvr_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
     "cvr_peer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "cvr_peer_close": (C.c_int, [C.c_int, C.c_void_p]),

@@ -369,6 +369,9 @@ int cvr_spmv_publish(cvr_handle_t* h, const double* x_dev, double* y_dev, const 
     p.n_dst = pub->n_dst;
     p.mode = pub->mode;
     p.row_offset = pub->row_offset;
+    p.needs = pub->needs;
+    p.clear_next = pub->clear_next;
+    p.chunk_any = pub->chunk_any;
     for (int k = 0; k < pub->n_dst; k++) {
         if (!pub->dst[k]) return fail(CVR_ERR_INVALID, "dst[%d] is NULL", k);
         p.dst[k] = pub->dst[k];
@@ -509,6 +512,27 @@ int cvr_get_kernel_timing(cvr_handle_t* h, double* total_seconds, int64_t* launc
     *total_seconds = total;
     *launches = (int64_t)(h->timing_used / 2);
     h->timing_used = 0;
+    return CVR_OK;
+}
+
+int cvr_column_footprint(cvr_handle_t* h, uint8_t* used_dev, void* cuda_stream)
+{
+    if (!h || !used_dev) return fail(CVR_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (cvr_launch_column_footprint(h->cols, h->nnz, used_dev, static_cast<cudaStream_t>(cuda_stream)) < 0)
+        return fail(CVR_ERR_CUDA, "footprint launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += 1;
+    return CVR_OK;
+}
+
+int cvr_chunk_needs(cvr_handle_t* h, const uint8_t* needs_dev, uint8_t* chunk_any_dev, void* cuda_stream)
+{
+    if (!h || !needs_dev || !chunk_any_dev) return fail(CVR_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (cvr_launch_chunk_needs(h->chunks, h->n_chunks, needs_dev, chunk_any_dev,
+                               static_cast<cudaStream_t>(cuda_stream)) < 0)
+        return fail(CVR_ERR_CUDA, "chunk-needs launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += 1;
     return CVR_OK;
 }
 

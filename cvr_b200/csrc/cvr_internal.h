@@ -46,7 +46,12 @@ struct CvrPublish {
     int32_t n_dst;                 // 0: do not publish
     int32_t mode;                  // bit 0: per-row stores at emit instead of the coalesced per-chunk push (A/B)
                                    // bit 1: do not re-publish 0.0 for the never-written rows
+                                   // bit 2: y IS this GPU's slice of the next x (no local copy; y[0] is foreign)
     int64_t row_offset;            // global row = row_offset + local row
+    const uint8_t* needs;          // needs[local row] bit p: destination p reads that x entry (NULL: all do)
+    const uint8_t* chunk_any;      // chunk_any[t] != 0: some row of chunk t's range has a reader elsewhere (NULL: all)
+    double* clear_next;            // y of the NEXT sweep: its accumulated rows are cleared by the epilogue
+                                   // (NULL: y itself).  Set when y aliases this GPU's slice of the next x.
     double* dst[CVR_MAX_PEERS];
 };
 
@@ -97,6 +102,11 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
                     const CvrBarrier* barrier = nullptr, unsigned int* done_counter = nullptr,
                     bool y_is_clear = false);
 int cvr_launch_peer_barrier(const CvrBarrier& b, cudaStream_t stream);
+// used[c] = 1 for every column id that occurs in cols[0..nnz)
+// chunk_any[t] = OR of needs[first_row..last_row] of chunk t
+int cvr_launch_chunk_needs(const CvrChunk* chunks, int32_t n_chunks, const uint8_t* needs, uint8_t* chunk_any,
+                           cudaStream_t stream);
+int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used, cudaStream_t stream);
 
 // resident warps per SM of the SpMV kernel in use (sizes the automatic chunk count)
 int cvr_spmv_resident_warps_per_sm();

@@ -258,9 +258,10 @@ __device__ __forceinline__ void store_row(const TileCtx& cx, int32_t row, double
     cx.y[row] = value;
     if (kPublish && cx.scatter) { // scattered 8-byte peer stores, row by row
         const int64_t g = cx.pub->row_offset + row;
+        const uint32_t nb = cx.pub->needs ? cx.pub->needs[row] : 0xffu;
 #pragma unroll
         for (int p = 0; p < CVR_MAX_PEERS; p++)
-            if (p < cx.pub->n_dst) cx.pub->dst[p][g] = value;
+            if (p < cx.pub->n_dst && ((nb >> p) & 1u)) cx.pub->dst[p][g] = value;
     }
 }
 
@@ -279,15 +280,19 @@ __device__ __forceinline__ void publish_chunk_rows(const TileCtx& cx, int32_t fi
     const CvrPublish& pub = *cx.pub;
     for (int32_t r0 = first_row + t; r0 <= last_row; r0 += 4 * 32) {
         double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = (r0 + 32 * u <= last_row) ? __ldcg(cx.y + r0 + 32 * u) : 0.0;
+        uint32_t nb[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            if (r0 + 32 * u > last_row) break;
+            const bool in = r0 + 32 * u <= last_row;
+            v[u] = in ? __ldcg(cx.y + r0 + 32 * u) : 0.0;
+            nb[u] = !in ? 0u : (pub.needs ? pub.needs[r0 + 32 * u] : 0xffu);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
             const int64_t g = pub.row_offset + r0 + 32 * u;
 #pragma unroll
             for (int p = 0; p < CVR_MAX_PEERS; p++)
-                if (p < pub.n_dst) pub.dst[p][g] = v[u];
+                if (p < pub.n_dst && ((nb[u] >> p) & 1u)) pub.dst[p][g] = v[u];
         }
     }
 }
@@ -572,7 +577,8 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
             const int32_t row = cp->tail[t];
             if (row != 0) atomicAdd(&y[row], carry); // row 0 = phantom row of unused lanes (carry 0.0)
         }
-        if (kPublish && !cx.scatter) publish_chunk_rows(cx, cx.first_row, chunk_last_row, t);
+        if (kPublish && !cx.scatter && (!pub.chunk_any || pub.chunk_any[chunk]))
+            publish_chunk_rows(cx, cx.first_row, chunk_last_row, t);
     }
 }
 
@@ -582,11 +588,15 @@ constexpr int TB_TMA = 9, TB_LDG = 8;
 // y is cleared only where it is accumulated (boundary rows) or never written (empty rows, row 0):
 // every other row is stored exactly once by the sweep.  Replaces an 8*(nRows+1)-byte memset.
 __global__ void cvr_clear_rows_kernel(double* __restrict__ y, const int32_t* __restrict__ boundary,
-                                      int32_t n_boundary, const int32_t* __restrict__ empty, int32_t n_empty)
+                                      int32_t n_boundary, const int32_t* __restrict__ empty, int32_t n_empty,
+                                      bool skip_row0)
 {
     const int32_t n = n_boundary + n_empty;
-    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        y[i < n_boundary ? boundary[i] : empty[i - n_boundary]] = 0.0;
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int32_t row = i < n_boundary ? boundary[i] : empty[i - n_boundary];
+        if (row == 0 && skip_row0) continue; // y aliases a slice of x: y[0] is the neighbour's last row
+        y[row] = 0.0;
+    }
 }
 
 // After the sweep of an iterated multi-GPU SpMV, ONE epilogue kernel does everything that has to
@@ -603,6 +613,8 @@ __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_
                                             const __grid_constant__ CvrBarrier bar, unsigned int* done_counter)
 {
     const bool publish_empty = (pub.mode & 2) == 0;
+    const bool aliased = (pub.mode & 4) != 0;
+    double* next_y = pub.clear_next ? pub.clear_next : y;
     const int32_t n = n_boundary + (publish_empty ? n_empty : 0);
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const bool b = i < n_boundary;
@@ -611,12 +623,16 @@ __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_
         double v = 0.0;
         if (b) {
             v = y[row];
-            y[row] = 0.0;
+            next_y[row] = 0.0;
+        } else if (aliased) {
+            y[row] = 0.0;       // never-written row of my own slice: drop whatever the buffer held
+            next_y[row] = 0.0;
         }
         const int64_t g = pub.row_offset + row;
+        const uint32_t nb = pub.needs ? pub.needs[row] : 0xffu;
 #pragma unroll
         for (int p = 0; p < CVR_MAX_PEERS; p++)
-            if (p < pub.n_dst) pub.dst[p][g] = v;
+            if (p < pub.n_dst && ((nb >> p) & 1u)) pub.dst[p][g] = v;
     }
     // ---- last block: flag barrier (see cvr_peer_barrier_kernel)
     __shared__ bool is_last;
@@ -706,7 +722,7 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
     } else if (rows.boundary && k != SpmvKernel::Window) {
         const int cb = (n_clear + 255) / 256;
         cvr_clear_rows_kernel<<<cb < 1184 ? (cb < 1 ? 1 : cb) : 1184, 256, 0, stream>>>(
-            y, rows.boundary, rows.n_boundary, rows.empty, rows.n_empty);
+            y, rows.boundary, rows.n_boundary, rows.empty, rows.n_empty, publish && (publish->mode & 4));
         launched++;
     } else if (cudaMemsetAsync(y, 0, sizeof(double) * (size_t)(n_rows + 1), stream) != cudaSuccess) {
         return -1;
@@ -754,6 +770,42 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launched;
+}
+
+namespace {
+__global__ void cvr_column_footprint_kernel(const int32_t* __restrict__ cols, int64_t nnz,
+                                            uint8_t* __restrict__ used)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
+        used[cols[i]] = 1; // benign race: every writer stores the same byte
+}
+} // namespace
+
+namespace {
+__global__ void cvr_chunk_needs_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
+                                       const uint8_t* __restrict__ needs, uint8_t* __restrict__ chunk_any)
+{
+    const int32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chunk >= T) return;
+    const int t = threadIdx.x & 31;
+    unsigned any = 0;
+    for (int32_t r = chunks[chunk].first_row + t; r <= chunks[chunk].last_row; r += 32) any |= needs[r];
+    any = __reduce_or_sync(0xffffffffu, any);
+    if (t == 0) chunk_any[chunk] = (uint8_t)any;
+}
+} // namespace
+
+int cvr_launch_chunk_needs(const CvrChunk* chunks, int32_t n_chunks, const uint8_t* needs, uint8_t* chunk_any,
+                           cudaStream_t stream)
+{
+    cvr_chunk_needs_kernel<<<(n_chunks * 32 + 127) / 128, 128, 0, stream>>>(chunks, n_chunks, needs, chunk_any);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used, cudaStream_t stream)
+{
+    cvr_column_footprint_kernel<<<148 * 16, 256, 0, stream>>>(cols, nnz, used);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int cvr_launch_peer_barrier(const CvrBarrier& b, cudaStream_t stream)

@@ -70,7 +70,7 @@ class PeerPublisher:
     64-byte IPC handles at set-up time.
     """
 
-    def __init__(self, matrix, cuts, rank: int, world: int, device_index: int, group=None):
+    def __init__(self, matrix, cuts, rank: int, world: int, device_index: int, group=None, sparse: bool = True):
         import ctypes as C
         from . import _lib
         if world > 8:
@@ -106,12 +106,39 @@ class PeerPublisher:
                 row.append(ptr.value)
                 self._opened.append(ptr.value)
             self.ptrs.append(row)
+        # who reads what: every rank marks the columns its shard touches, the marks are exchanged
+        # once, and a row is then published only to the ranks whose mark is set (plus its owner)
+        self.needs = None
+        if sparse and world > 1:
+            used = torch.zeros(self.n_rows + 1, dtype=torch.uint8, device=torch.device("cuda", device_index))
+            _lib.check(self._lib.cvr_column_footprint(matrix._h, used.data_ptr(), 0))
+            torch.cuda.synchronize(device_index)
+            lo, hi = self.cuts[rank], self.cuts[rank + 1]
+            needs = torch.zeros(max(hi - lo, 1) + 1, dtype=torch.uint8, device=used.device)  # [0] = phantom row
+            # to rank q: my marks on q's rows; from rank q: q's marks on MY rows
+            parts = [used[self.cuts[q]:self.cuts[q + 1]].contiguous() for q in range(world)]
+            recv = [torch.empty(hi - lo, dtype=torch.uint8, device=used.device) for _ in range(world)]
+            dist.all_to_all(recv, parts, group=group)
+            for q in range(world):
+                needs[1:1 + hi - lo] |= (recv[q] << q)
+            del used, parts, recv
+            needs[1:] &= 0xFF ^ (1 << rank)  # own rows are written in place (y aliases my slice of x)
+            self.needs = needs
+            self.chunk_any = torch.zeros(matrix.n_chunks, dtype=torch.uint8, device=needs.device)
+            _lib.check(self._lib.cvr_chunk_needs(matrix._h, needs.data_ptr(), self.chunk_any.data_ptr(), 0))
+            torch.cuda.synchronize(device_index)
+            self.needed_rows = [int(((needs[1:] >> q) & 1).sum()) for q in range(world)]
         self.pub = []
         for parity in (0, 1):
             p = _lib.CvrPublish()
             p.n_dst = world
             p.mode = int(os.environ.get("CVR_PUBLISH_MODE", "0"))
             p.row_offset = self.cuts[rank] - 1
+            p.needs = self.needs.data_ptr() if self.needs is not None else None
+            p.chunk_any = self.chunk_any.data_ptr() if self.needs is not None else None
+            # the sweep writes y straight into my slice of the next x: no local copy of my own rows
+            p.mode |= 4
+            p.clear_next = self.ptrs[rank][1 - parity] + 8 * (self.cuts[rank] - 1)
             for r in range(world):
                 p.dst[r] = self.ptrs[r][parity]
             self.pub.append(p)
@@ -134,26 +161,44 @@ class PeerPublisher:
         for p in self.pub:
             p.mode &= ~2
         self.x_tensor().copy_(x)
+        # the first sweep after a reset runs its own clearing kernel on its y (= my slice of the other
+        # buffer); nothing else to prepare
         torch.cuda.synchronize(self.dev)
         dist.barrier()
 
-    def step(self, y_local: torch.Tensor, stream: int) -> None:
-        """One iteration x <- A x.  y_local must be the same buffer in consecutive calls (the epilogue
-        kernel leaves its accumulated rows cleared for the next sweep)."""
+    def step(self, y_local, stream: int) -> None:
+        """One iteration x <- A x.  y_local is unused (kept for call compatibility with the all-gather
+        path): the sweep writes this rank's y directly into its slice of the next x buffer."""
         cur, nxt = self.k % 2, (self.k + 1) % 2
         pub = self.pub[nxt]
         if self.k == self._reset_k + 2:  # both x buffers now hold 0.0 at the never-written rows
             for p in self.pub:
                 p.mode |= 2
         self.epoch += 1
-        same_y = self._last_y == y_local.data_ptr()
-        self.m.spmv_publish(self.ptrs[self.rank][cur], y_local, pub, self._flags, self.rank, self.world,
-                            self.epoch, same_y, stream)
-        self._last_y = y_local.data_ptr()
+        y_alias = self.ptrs[self.rank][nxt] + 8 * (self.cuts[self.rank] - 1)  # y[r] == x_next[lo - 1 + r]
+        self.m.spmv_publish(self.ptrs[self.rank][cur], y_alias, pub, self._flags, self.rank, self.world,
+                            self.epoch, self.k > self._reset_k, stream)
         self.k += 1
 
+    def full_x(self) -> torch.Tensor:
+        """The complete current x on every rank.  With footprint-sparse publishing a rank's own
+        buffer only holds the entries it reads (plus its own rows), so the full vector is assembled
+        from the owners' slices -- one broadcast per rank, outside the iteration loop."""
+        torch.cuda.synchronize(self.dev)
+        mine = self.x_tensor()
+        out = torch.zeros_like(mine)
+        for r in range(self.world):
+            lo, hi = self.cuts[r], self.cuts[r + 1]
+            piece = mine[lo:hi].clone() if r == self.rank else torch.empty(hi - lo, dtype=torch.float64, device=mine.device)
+            dist.broadcast(piece, src=r)
+            out[lo:hi] = piece
+        return out
+
     def bytes_sent_per_iteration(self) -> int:
-        return 8 * self.n_local * (self.world - 1)
+        """Bytes this rank stores into PEER memory per iteration."""
+        if self.needs is None:
+            return 8 * self.n_local * (self.world - 1)
+        return 8 * sum(n for q, n in enumerate(self.needed_rows) if q != self.rank)
 
     def close(self) -> None:
         torch.cuda.synchronize(self.dev)

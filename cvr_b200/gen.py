@@ -154,3 +154,59 @@ def random_sparse(n_rows: int, n_cols: int, nnz: int, device="cpu", seed: int = 
         cc = torch.randint(1, n_cols + 1, (rr.shape[0],), generator=g, device=dev, dtype=torch.int64)
         r, c = torch.cat([r, rr]), torch.cat([c, cc])
     return _finish(r * (n_cols + 1) + c, n_rows, n_cols, g)
+
+
+def rmat_shard(scale: int, edge_factor: int, rank: int, world: int, device="cpu", seed: int = 3,
+               abcd=(0.57, 0.19, 0.19, 0.05), row_normalise: bool = True, batch: int = 1 << 26):
+    """Row shard `rank` of `world` of an R-MAT matrix too large to build on one GPU (config 5:
+    scale 28, 4.3e9 edges).  Every rank draws the same edge stream twice from per-batch seeds
+    (pass 1: row histogram -> nnz-balanced cuts, the rule of cvr_b200.shard; pass 2: keep only the
+    rows it owns), so no edge ever leaves the GPU that generated it and no rank holds more than its
+    own shard.  Returns (DeviceCsr with LOCAL rows 1..n_local and GLOBAL columns, cuts list,
+    entries in this shard before padding)."""
+    dev = torch.device(device)
+    n = 1 << scale
+    total = edge_factor << scale
+    a, b, c, _ = abcd
+    n_batches = (total + batch - 1) // batch
+
+    def draw(i):
+        g = torch.Generator(device=dev)
+        g.manual_seed(MASTER_SEED + 7919 * int(seed) + i)
+        m = min(batch, total - i * batch)
+        r = torch.zeros(m, dtype=torch.int64, device=dev)
+        col = torch.zeros(m, dtype=torch.int64, device=dev)
+        for _level in range(scale):
+            u = torch.rand(m, generator=g, device=dev, dtype=torch.float32)
+            r = (r << 1) | (u >= a + b).to(torch.int64)
+            col = (col << 1) | (((u >= a) & (u < a + b)) | (u >= a + b + c)).to(torch.int64)
+        return r + 1, col + 1
+
+    counts = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+    for i in range(n_batches):
+        r, _ = draw(i)
+        counts += torch.bincount(r, minlength=n + 2)
+        del r
+    ends = torch.cumsum(counts, 0)  # ends[r] = edges in rows <= r
+    del counts
+    cuts = [1]
+    for gidx in range(1, world):
+        target = torch.tensor([(total * gidx) // world], dtype=torch.int64, device=dev)
+        # first row whose start (= ends[row-1]) is >= target
+        row = int(torch.searchsorted(ends, target, right=False)) + 1
+        cuts.append(min(max(row, cuts[-1]), n + 1))
+    cuts.append(n + 1)
+    del ends
+    lo, hi = cuts[rank], cuts[rank + 1]
+    kept = []
+    for i in range(n_batches):
+        r, col = draw(i)
+        sel = (r >= lo) & (r < hi)
+        kept.append(torch.unique((r[sel] - lo + 1) * (n + 1) + col[sel]))
+        del r, col, sel
+    n_local = max(hi - lo, 1)
+    g = _gen(dev, 1000 + seed * 131 + rank)
+    keys = torch.cat(kept) if kept else torch.zeros(0, dtype=torch.int64, device=dev)
+    del kept
+    d = _finish(keys, n_local, n, g, row_normalise)
+    return d, cuts, d.nnz_true

@@ -154,8 +154,16 @@ int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* c
 typedef struct cvr_publish {
     int32_t n_dst;       /* 1..CVR_MAX_PEERS destinations, own buffer included */
     int32_t mode;        /* bit 0: per-row stores instead of the coalesced per-chunk push (A/B);
-                            bit 1: skip the 0.0 for never-written rows (set from the 3rd iteration on) */
+                            bit 1: skip the 0.0 for never-written rows (set from the 3rd iteration on);
+                            bit 2: y_dev IS this GPU's own slice of the next x (x_next + row_offset), so
+                                   own rows need no copy; then leave this GPU's bit out of `needs`, and
+                                   set clear_next = x_current + row_offset (the next iteration's y) */
     int64_t row_offset;  /* global row id = row_offset + local row (first cut - 1) */
+    const uint8_t* needs; /* device array, needs[local row] bit p set: destination p reads x[that row]
+                             (its shard has a nonzero in that column); NULL = every destination */
+    const uint8_t* chunk_any; /* device array from cvr_chunk_needs (chunks with nothing to send skip
+                                 the push), or NULL */
+    double* clear_next;  /* NULL, or the y of the NEXT iteration (see mode bit 2) */
     double* dst[CVR_MAX_PEERS];
 } cvr_publish_t;
 /* One iteration = at most three kernels on cuda_stream: [clear the accumulated rows of y, unless
@@ -166,6 +174,12 @@ typedef struct cvr_publish {
 int cvr_spmv_publish(cvr_handle_t* h, const double* x_dev, double* y_dev, const cvr_publish_t* pub,
                      void* const* flag_arrays, int32_t rank, int32_t n_ranks, uint32_t epoch,
                      int32_t y_is_clear, void* cuda_stream);
+/* used_dev[c] = 1 for every column id c (0..n_cols) that occurs in the shard: the x entries this
+ * GPU actually reads.  Exchanged once, it lets every GPU publish a row only to the peers that
+ * read it (a banded matrix then sends halos, not the whole vector). */
+int cvr_column_footprint(cvr_handle_t* h, uint8_t* used_dev, void* cuda_stream);
+/* chunk_any_dev[t] (n_chunks bytes) = OR of needs_dev over the row range of chunk t */
+int cvr_chunk_needs(cvr_handle_t* h, const uint8_t* needs_dev, uint8_t* chunk_any_dev, void* cuda_stream);
 int cvr_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char handle[64]); /* zero-filled */
 int cvr_peer_open(int device, const unsigned char handle[64], void** dev_ptr);
 int cvr_peer_close(int device, void* dev_ptr);

@@ -49,7 +49,7 @@ def _worker(rank, world, port, iters, out, fused=False):
         for _ in range(iters):
             pp.step(y, stream)
         torch.cuda.synchronize()
-        x = pp.x_tensor().clone()
+        x = pp.full_x()
         pp.close()
     else:
         iterate(lambda xx, yy: m.spmv_device(xx, yy, stream), ex, x, y, iters)

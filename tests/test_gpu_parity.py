@@ -133,6 +133,26 @@ def test_auto_chunks_and_device_csr_entry(cvr):
                                                + 8 * (csr.n_cols + 1) + 8 * (csr.n_rows + 1))
 
 
+def test_64bit_row_delimiters_entry(cvr):
+    """row_delim64 is the entry for nnz >= 2^31 (config 5 shards); exercise it at a small size."""
+    import torch
+    from cvr_b200 import gen
+    d = gen.rmat(12, 16, device="cuda", seed=48)
+    csr = to_oracle_csr(d)
+    d.row_delim = d.row_delim.to(torch.int64)
+    x = np.random.default_rng(5).uniform(-1, 1, csr.n_cols + 1)
+    with cvr.CvrMatrix(d, 300) as m:
+        assert_structure_equal(m.export(), oracle.convert(csr, 300, "port", fill_missing_tail=True), "rd64")
+        y, _ = m.spmv(x)
+        assert_y_close(y, csr, x, "rd64")
+    h = d.to_host()
+    h64 = cvr.CsrMatrix(h.n_rows, h.n_cols, h.val, h.col, h.row_delim.astype(np.int32), h.nnz_true)
+    h64.row_delim = h.row_delim.astype(np.int64)
+    with cvr.CvrMatrix(h64, 7) as m:
+        y, _ = m.spmv(x)
+        assert_y_close(y, csr, x, "rd64 host")
+
+
 def test_full_size_properties_linearity_and_checksum(cvr):
     """Config-2-sized input (1M rows, 26.5M nnz): too slow for the scalar port in a unit test,
     so check size-independent properties: A(ax+by) = aAx + bAy row by row within the bound, and
