@@ -240,6 +240,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         cuts = shard.partition_rows_by_nnz_torch(full.row_delim, world) if world > 1 else [1, n_rows_total + 1]
         mine = shard.shard_device_csr(full, cuts[rank], cuts[rank + 1]) if world > 1 else full
     keep_host = full.to_host() if (full is not None and rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    keep_csr = None
+    if full is not None and world == 1 and not args.no_cusparse and full.nnz < 600_000_000:
+        keep_csr = (full.row_delim.to(torch.int64).clone(), full.col.to(torch.int64), full.val.clone())
     del full
     torch.cuda.synchronize()
 
@@ -353,6 +356,39 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_gflops = 2.0 * nnz_true_total / float(e2e_s.item()) / 1e9
 
+    # ---- context: cuSPARSE CSR SpMV (through torch.sparse) on the same matrix, same x -- the
+    # library baseline a GPU user would reach for; not part of the headline
+    cusparse = None
+    if world == 1 and keep_csr is not None and not args.no_cusparse:
+        try:
+            crow, ccol, cval = keep_csr
+            A = torch.sparse_csr_tensor(crow, ccol, cval, size=(info["n_rows"] + 1, n_cols + 1))
+            for _ in range(3):
+                yy = A @ x
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                if flush is not None:
+                    flush.fill_(1)
+                yy = A @ x
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            if flush is not None:  # subtract the flush, measured alone
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(args.steps):
+                    flush.fill_(1)
+                f1.record()
+                torch.cuda.synchronize()
+                ms -= f0.elapsed_time(f1) / args.steps
+            cusparse = {"gflops": 2.0 * nnz_true_total / (ms * 1e-3) / 1e9, "ms_per_spmv": ms,
+                        "what": "torch.sparse_csr (cuSPARSE) y = A @ x, fp64, same matrix and x"}
+            del A, yy
+        except Exception as ex:  # context only: never fail the bench on it
+            cusparse = {"error": str(ex)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": gflops, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -381,6 +417,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "extra": {"step_gbs": info["algorithmic_bytes"] * world / (ms_per_step * 1e-3) / 1e9 if scaling == "weak"
                       else None,
                       "peer_bytes_sent_per_step_rank0": publisher.bytes_sent_per_iteration() if publisher else None,
+                      "cusparse_csr": cusparse,
                       "convert_seconds_device": info["convert_seconds"],
                       "create_seconds": info["create_seconds"], "n_records": info["n_records"]},
         }
@@ -408,6 +445,7 @@ def main():
     ap.add_argument("--workload", default="fem")
     ap.add_argument("--chunks", type=int, default=0, help="CVR chunks per GPU (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cusparse", action="store_true", help="skip the cuSPARSE CSR context measurement")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="peer exchange: publish every row to every GPU instead of only to the GPUs that read it")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

@@ -289,6 +289,9 @@ int cvr_device_init(int device)
         return fail(CVR_ERR_INVALID, "device %d out of range [0, %d)", device, n_dev);
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaFree(nullptr));
+    cvr_preload_convert_kernels();
+    cvr_preload_spmv_kernels();
+    cudaGetLastError();
     return CVR_OK;
 }
 

@@ -305,6 +305,16 @@ __global__ void cvr_collect_rows_kernel(const RdT* __restrict__ rd, int64_t n_ro
 
 } // namespace
 
+void cvr_preload_convert_kernels()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, cvr_schedule_kernel<int32_t>);
+    cudaFuncGetAttributes(&a, cvr_schedule_kernel<int64_t>);
+    cudaFuncGetAttributes(&a, cvr_permute_kernel);
+    cudaFuncGetAttributes(&a, cvr_mark_boundary_kernel);
+    cudaFuncGetAttributes(&a, cvr_collect_rows_kernel<int32_t>);
+}
+
 int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t* rd32, const int64_t* rd64,
                         int64_t n_rows, CvrRowLists* out, cudaStream_t stream)
 {

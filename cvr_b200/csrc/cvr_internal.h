@@ -110,3 +110,7 @@ int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used,
 
 // resident warps per SM of the SpMV kernel in use (sizes the automatic chunk count)
 int cvr_spmv_resident_warps_per_sm();
+
+// force-load the kernels' module so the first timed call does not pay CUDA's lazy loading
+void cvr_preload_convert_kernels();
+void cvr_preload_spmv_kernels();

@@ -338,6 +338,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "[%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 
+// acc = fma(a, x, acc) under a predicate: one ISETP + one predicated DFMA (the plain C++ `if` compiles
+// to an unconditional DFMA plus two FSELs per chain step)
+__device__ __forceinline__ void fma_if(double& acc, double a, double x, uint32_t cond)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p fma.rn.f64 %0, %1, %2, %0;\n\t}"
+        : "+d"(acc) : "d"(a), "d"(x), "r"(cond));
+}
+
 // flag bytes (0/1) of a 32-bit word -> 4-bit mask
 __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return ((w * 0x00204081u) >> 21) & 0xfu; }
 
@@ -529,9 +537,11 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
             const uint32_t after = ~((1u << b_last) - 1u);      // steps from the last flag on
             double head = 0.0, tailsum = 0.0;
 #pragma unroll
+            const uint32_t after_m = mask ? after : 0u;
+#pragma unroll
             for (int b = 0; b < TB; b++) {
-                if ((below >> b) & 1u) head = fma(a[b], xv[b], head);
-                if (mask && ((after >> b) & 1u)) tailsum = fma(a[b], xv[b], tailsum);
+                fma_if(head, a[b], xv[b], below & (1u << b));
+                fma_if(tailsum, a[b], xv[b], after_m & (1u << b));
             }
             // segments strictly between two flags of the same thread (short rows): emit in place
             if (b_last > b_first) {
@@ -582,7 +592,11 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
     }
 }
 
-constexpr int TB_TMA = 9, TB_LDG = 8;
+#ifndef CVR_TB_TMA
+#define CVR_TB_TMA 9
+#endif
+constexpr int TB_TMA = CVR_TB_TMA, TB_LDG = 8;
+static_assert(TB_TMA % 2 == 1, "the TMA tile needs an odd number of steps per walker (bank layout)");
 
 // ---- small helper kernels around the sweep
 // y is cleared only where it is accumulated (boundary rows) or never written (empty rows, row 0):
@@ -689,6 +703,13 @@ SpmvKernel selected_kernel()
 }
 
 } // namespace
+
+void cvr_preload_spmv_kernels()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<true, TB_TMA, false>);
+    cudaFuncGetAttributes(&a, cvr_clear_rows_kernel);
+}
 
 // resident warps per SM of the selected kernel (used to size the automatic chunk count)
 int cvr_spmv_resident_warps_per_sm()
