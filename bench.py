@@ -224,7 +224,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if big_rmat is not None:
         # config 5: too large to build on one GPU -- every rank generates only its own row shard
         from cvr_b200 import gen
-        mine, cuts, nt = gen.rmat_shard(big_rmat, 16, rank, world, dev, row_normalise=True)
+        mine, cuts, nt = gen.rmat_shard(big_rmat, 16, rank, world, dev, row_normalise=True,
+                                        row_weight=args.row_weight)
         tot = torch.tensor([nt], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(tot)
@@ -237,7 +238,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         full, desc, scaling = make_workload(args.workload, world, dev, row_normalise=True)
         nnz_true_total = full.nnz_true
         n_rows_total, n_cols = full.n_rows, full.n_cols
-        cuts = shard.partition_rows_by_nnz_torch(full.row_delim, world) if world > 1 else [1, n_rows_total + 1]
+        cuts = (shard.partition_rows_by_nnz_torch(full.row_delim, world, args.row_weight) if world > 1
+                else [1, n_rows_total + 1])
         mine = shard.shard_device_csr(full, cuts[rank], cuts[rank + 1]) if world > 1 else full
     keep_host = full.to_host() if (full is not None and rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     keep_csr = None
@@ -396,6 +398,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "n_rows": n_rows_total, "nnz": nnz_true_total,
                        "chunks_per_gpu": info["n_chunks"], "iterated_x_from_y": iterated,
+                       "shard_balance": ("nnz" if not args.row_weight else f"nnz + {args.row_weight:g} per non-empty row")
+                       if world > 1 else None,
                        "l2": "inputs exceed L2 (no flush)" if flush is None else "L2 flushed between steps (384 MB write, untimed)",
                        "step": "clear accumulated rows + cvr_spmv_kernel" + (
                            (" (publishes y rows into every peer's x over NVLink) + accumulated-rows publish + flag barrier"
@@ -446,6 +450,8 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="CVR chunks per GPU (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cusparse", action="store_true", help="skip the cuSPARSE CSR context measurement")
+    ap.add_argument("--row-weight", type=float, default=0.0,
+                    help="N > 1: balance shards by nnz + W per non-empty row instead of nnz alone (0 = nnz, the spec)")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="peer exchange: publish every row to every GPU instead of only to the GPUs that read it")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

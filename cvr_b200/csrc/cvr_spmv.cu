@@ -536,7 +536,6 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
             const uint32_t below = (1u << b_first) - 1u;        // steps before the first flag
             const uint32_t after = ~((1u << b_last) - 1u);      // steps from the last flag on
             double head = 0.0, tailsum = 0.0;
-#pragma unroll
             const uint32_t after_m = mask ? after : 0u;
 #pragma unroll
             for (int b = 0; b < TB; b++) {

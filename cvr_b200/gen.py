@@ -157,7 +157,8 @@ def random_sparse(n_rows: int, n_cols: int, nnz: int, device="cpu", seed: int = 
 
 
 def rmat_shard(scale: int, edge_factor: int, rank: int, world: int, device="cpu", seed: int = 3,
-               abcd=(0.57, 0.19, 0.19, 0.05), row_normalise: bool = True, batch: int = 1 << 26):
+               abcd=(0.57, 0.19, 0.19, 0.05), row_normalise: bool = True, batch: int = 1 << 26,
+               row_weight: float = 0.0):
     """Row shard `rank` of `world` of an R-MAT matrix too large to build on one GPU (config 5:
     scale 28, 4.3e9 edges).  Every rank draws the same edge stream twice from per-batch seeds
     (pass 1: row histogram -> nnz-balanced cuts, the rule of cvr_b200.shard; pass 2: keep only the
@@ -187,11 +188,14 @@ def rmat_shard(scale: int, edge_factor: int, rank: int, world: int, device="cpu"
         r, _ = draw(i)
         counts += torch.bincount(r, minlength=n + 2)
         del r
-    ends = torch.cumsum(counts, 0)  # ends[r] = edges in rows <= r
+    if row_weight:  # balance nnz + row_weight per non-empty row (shard.partition_rows_by_nnz)
+        counts = counts + ((counts > 0).to(torch.float64) * float(row_weight)).to(torch.int64)
+    ends = torch.cumsum(counts, 0)  # ends[r] = (weighted) edges in rows <= r
     del counts
+    weighted_total = int(ends[-1])
     cuts = [1]
     for gidx in range(1, world):
-        target = torch.tensor([(total * gidx) // world], dtype=torch.int64, device=dev)
+        target = torch.tensor([(weighted_total * gidx) // world], dtype=torch.int64, device=dev)
         # first row whose start (= ends[row-1]) is >= target
         row = int(torch.searchsorted(ends, target, right=False)) + 1
         cuts.append(min(max(row, cuts[-1]), n + 1))

@@ -14,11 +14,18 @@ import numpy as np
 from .csr import CsrMatrix
 
 
-def partition_rows_by_nnz(row_delim, n_parts: int) -> np.ndarray:
+def partition_rows_by_nnz(row_delim, n_parts: int, row_weight: float = 0.0) -> np.ndarray:
     """Cut points c[0..G] over the 1-based rows: part g owns rows c[g] .. c[g+1]-1, c[0] = 1,
-    c[G] = n_rows + 1.  row_delim is the n_rows+2 array of the 1-based CSR."""
+    c[G] = n_rows + 1.  row_delim is the n_rows+2 array of the 1-based CSR.
+    row_weight = 0 balances nnz (the north star's rule); row_weight = w balances nnz + w per non-empty
+    row, the measured cost model of the SpMV sweep on skewed matrices (a row costs about 3 nonzeros:
+    record, y store, clearing -- DESIGN.md section 4)."""
     rd = np.asarray(row_delim).astype(np.int64)
     n_rows = rd.shape[0] - 2
+    if row_weight:
+        extra = np.zeros_like(rd)
+        extra[1:] = np.cumsum((np.diff(rd) > 0) * float(row_weight)).astype(np.int64)
+        rd = rd + extra
     nnz = int(rd[-1])
     cuts = np.empty(n_parts + 1, dtype=np.int64)
     cuts[0], cuts[n_parts] = 1, n_rows + 1
@@ -65,11 +72,15 @@ def gather_layout(cuts) -> tuple[np.ndarray, np.ndarray]:
     return cuts[:-1].copy(), (cuts[1:] - cuts[:-1]).copy()
 
 
-def partition_rows_by_nnz_torch(row_delim, n_parts: int):
+def partition_rows_by_nnz_torch(row_delim, n_parts: int, row_weight: float = 0.0):
     """partition_rows_by_nnz on a torch tensor (any device); returns a python list of ints."""
     import torch
     rd = row_delim.to(torch.int64)
     n_rows = rd.shape[0] - 2
+    if row_weight:
+        extra = torch.zeros_like(rd)
+        extra[1:] = torch.cumsum(((rd[1:] - rd[:-1]) > 0).to(torch.float64) * float(row_weight), 0).to(torch.int64)
+        rd = rd + extra
     nnz = int(rd[-1])
     cuts = [1]
     for g in range(1, n_parts):
