@@ -72,6 +72,8 @@ SIGNATURES = {
     "cvr_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
     "cvr_peer_barrier": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
     "cvr_export": (C.c_int, [C.c_void_p, C.POINTER(CvrArrays)]),
+    "cvr_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cvr_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "cvr_get_info": (C.c_int, [C.c_void_p, C.POINTER(CvrInfo)]),
     "cvr_device_vectors": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cvr_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),

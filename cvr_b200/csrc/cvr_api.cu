@@ -604,6 +604,138 @@ int cvr_peer_barrier(int device, void* const* flag_arrays, int32_t rank, int32_t
     return CVR_OK;
 }
 
+// ---- serialisation of a converted matrix: the conversion is paid once
+namespace {
+const char CVR_FILE_MAGIC[8] = {'C', 'V', 'R', 'B', '2', '0', '0', 1};
+struct CvrFileHeader {
+    char magic[8];
+    int64_t n_rows, n_cols, nnz, record_ints, n_records;
+    int32_t n_chunks, n_boundary, n_empty, chunk_bytes;
+};
+
+int copy_out(FILE* f, const void* dev, size_t bytes, std::vector<char>& buf)
+{
+    for (size_t off = 0; off < bytes; off += buf.size()) {
+        const size_t n = bytes - off < buf.size() ? bytes - off : buf.size();
+        if (cudaMemcpy(buf.data(), static_cast<const char*>(dev) + off, n, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(CVR_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (fwrite(buf.data(), 1, n, f) != n) return fail(CVR_ERR_INVALID, "short write");
+    }
+    return CVR_OK;
+}
+
+int copy_in(FILE* f, void* dev, size_t bytes, std::vector<char>& buf)
+{
+    for (size_t off = 0; off < bytes; off += buf.size()) {
+        const size_t n = bytes - off < buf.size() ? bytes - off : buf.size();
+        if (fread(buf.data(), 1, n, f) != n) return fail(CVR_ERR_INVALID, "truncated CVR file");
+        if (cudaMemcpy(static_cast<char*>(dev) + off, buf.data(), n, cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail(CVR_ERR_CUDA, "host->device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    return CVR_OK;
+}
+} // namespace
+
+int cvr_save(cvr_handle_t* h, const char* path)
+{
+    if (!h || !path) return fail(CVR_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(CVR_ERR_INVALID, "cannot open %s for writing", path);
+    CvrFileHeader hd{};
+    memcpy(hd.magic, CVR_FILE_MAGIC, 8);
+    hd.n_rows = h->n_rows;
+    hd.n_cols = h->n_cols;
+    hd.nnz = h->nnz;
+    hd.record_ints = h->record_ints;
+    hd.n_records = h->n_records;
+    hd.n_chunks = h->n_chunks;
+    hd.n_boundary = h->rows.n_boundary;
+    hd.n_empty = h->rows.n_empty;
+    hd.chunk_bytes = (int32_t)sizeof(CvrChunk);
+    std::vector<char> buf((size_t)32 << 20);
+    int rc = fwrite(&hd, sizeof(hd), 1, f) == 1 ? CVR_OK : fail(CVR_ERR_INVALID, "short write");
+    if (rc == CVR_OK) rc = copy_out(f, h->vals, sizeof(double) * (size_t)h->nnz, buf);
+    if (rc == CVR_OK) rc = copy_out(f, h->cols, sizeof(int32_t) * (size_t)h->nnz, buf);
+    if (rc == CVR_OK) rc = copy_out(f, h->record, sizeof(int32_t) * (size_t)h->record_ints, buf);
+    if (rc == CVR_OK) rc = copy_out(f, h->chunks, sizeof(CvrChunk) * (size_t)h->n_chunks, buf);
+    if (rc == CVR_OK) rc = copy_out(f, h->rows.boundary, sizeof(int32_t) * (size_t)h->rows.n_boundary, buf);
+    if (rc == CVR_OK) rc = copy_out(f, h->rows.empty, sizeof(int32_t) * (size_t)h->rows.n_empty, buf);
+    if (fclose(f) != 0 && rc == CVR_OK) rc = fail(CVR_ERR_INVALID, "close failed on %s", path);
+    return rc;
+}
+
+int cvr_load(const char* path, int device, cvr_handle_t** out)
+{
+    if (!path || !out) return fail(CVR_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    int rc = cvr_device_init(device);
+    if (rc != CVR_OK) return rc;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(CVR_ERR_INVALID, "cannot open %s", path);
+    const double t0 = wall_seconds();
+    CvrFileHeader hd{};
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, CVR_FILE_MAGIC, 8) != 0 ||
+        hd.chunk_bytes != (int32_t)sizeof(CvrChunk) || hd.nnz < 16 || hd.nnz % 16 || hd.n_chunks < 1 ||
+        hd.record_ints != cvr_record_ints(hd.n_rows, hd.n_chunks)) {
+        fclose(f);
+        return fail(CVR_ERR_INVALID, "%s is not a CVR file of this library version", path);
+    }
+    cvr_handle* h = new (std::nothrow) cvr_handle();
+    if (!h) {
+        fclose(f);
+        return fail(CVR_ERR_INVALID, "out of host memory");
+    }
+    h->device = device;
+    h->n_rows = hd.n_rows;
+    h->n_cols = hd.n_cols;
+    h->nnz = hd.nnz;
+    h->n_chunks = hd.n_chunks;
+    h->record_ints = hd.record_ints;
+    h->n_records = hd.n_records;
+    h->rows.n_boundary = hd.n_boundary;
+    h->rows.n_empty = hd.n_empty;
+    std::vector<char> buf((size_t)32 << 20);
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->vals, (size_t)h->nnz)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->cols, (size_t)h->nnz)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->record, (size_t)h->record_ints)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->chunks, (size_t)h->n_chunks)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->rows.boundary, (size_t)hd.n_boundary + 1)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->rows.empty, (size_t)hd.n_empty + 1)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->x, (size_t)h->n_cols + 1)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->y, (size_t)h->n_rows + 1)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) {
+        fclose(f);
+        delete h;
+        return fail(CVR_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e));
+    }
+    rc = copy_in(f, h->vals, sizeof(double) * (size_t)h->nnz, buf);
+    if (rc == CVR_OK) rc = copy_in(f, h->cols, sizeof(int32_t) * (size_t)h->nnz, buf);
+    if (rc == CVR_OK) rc = copy_in(f, h->record, sizeof(int32_t) * (size_t)h->record_ints, buf);
+    if (rc == CVR_OK) rc = copy_in(f, h->chunks, sizeof(CvrChunk) * (size_t)h->n_chunks, buf);
+    if (rc == CVR_OK) rc = copy_in(f, h->rows.boundary, sizeof(int32_t) * (size_t)hd.n_boundary, buf);
+    if (rc == CVR_OK) rc = copy_in(f, h->rows.empty, sizeof(int32_t) * (size_t)hd.n_empty, buf);
+    fclose(f);
+    if (rc != CVR_OK) {
+        delete h;
+        return rc;
+    }
+    h->host_chunks.resize((size_t)h->n_chunks);
+    if (cudaMemcpy(h->host_chunks.data(), h->chunks, sizeof(CvrChunk) * (size_t)h->n_chunks,
+                   cudaMemcpyDeviceToHost) != cudaSuccess) {
+        delete h;
+        return fail(CVR_ERR_CUDA, "descriptor copy failed");
+    }
+    h->create_seconds = wall_seconds() - t0;
+    *out = h;
+    return CVR_OK;
+}
+
 void cvr_destroy(cvr_handle_t* h) { delete h; }
 
 } // extern "C"

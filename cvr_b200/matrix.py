@@ -11,6 +11,7 @@ the CUDA kernels of libcvr_b200.so.  Without that library, or without a GPU, cal
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -76,6 +77,21 @@ class CvrMatrix:
         _lib.check(rc)
         self.n_rows, self.n_cols, self.nnz = csr.n_rows, csr.n_cols, csr.nnz
         self.nnz_true = getattr(csr, "nnz_true", csr.nnz)
+
+    # -- serialisation
+    def save(self, path: str) -> None:
+        _lib.check(self._lib.cvr_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "CvrMatrix":
+        """A matrix converted earlier (CvrMatrix.save): no CSR, no conversion."""
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        _lib.check(self._lib.cvr_load(os.fsencode(path), int(device), C.byref(self._h)))
+        i = self.info
+        self.n_rows, self.n_cols, self.nnz, self.nnz_true = i["n_rows"], i["n_cols"], i["nnz"], i["nnz"]
+        return self
 
     # -- lifetime
     def close(self) -> None:

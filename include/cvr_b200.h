@@ -192,6 +192,12 @@ int cvr_peer_barrier(int device, void* const* flag_arrays, int32_t rank, int32_t
 /* Bit-exact gate: copy the CVR structure arrays back in the reference layout. */
 int cvr_export(cvr_handle_t* h, cvr_arrays_t* host_out);
 
+/* Save / load a converted matrix (device CVR arrays, chunk descriptors, row lists) so that the
+ * conversion is paid once -- the paper's "iterations to amortise" drops to the load time.  The file
+ * is a little-endian dump tied to this library version; cvr_load fails on anything else. */
+int cvr_save(cvr_handle_t* h, const char* path);
+int cvr_load(const char* path, int device, cvr_handle_t** out);
+
 int cvr_get_info(cvr_handle_t* h, cvr_info_t* info);
 
 /* Device pointers of the handle's x / y scratch vectors (n_cols+1 / n_rows+1

@@ -133,6 +133,30 @@ def test_auto_chunks_and_device_csr_entry(cvr):
                                                + 8 * (csr.n_cols + 1) + 8 * (csr.n_rows + 1))
 
 
+def test_save_load_round_trip(cvr, tmp_path):
+    """cvr_save / cvr_load: the reloaded matrix exports the same structure bit for bit and gives the
+    same y (conversion skipped)."""
+    from cvr_b200 import gen
+    d = gen.random_sparse(5000, 4000, 40000, seed=49, empty_frac=0.15, long_rows=2, long_len=1500)
+    csr = to_oracle_csr(d)
+    x = np.random.default_rng(6).uniform(-1, 1, csr.n_cols + 1)
+    p = str(tmp_path / "m.cvr")
+    with cvr.CvrMatrix(d.to_host(), 200) as m:
+        a = m.export()
+        ya, _ = m.spmv(x)
+        m.save(p)
+    with cvr.CvrMatrix.load(p) as m2:
+        assert m2.info["convert_seconds"] == 0.0 and m2.n_chunks == 200
+        assert_structure_equal(m2.export(), a, "reloaded")
+        yb, _ = m2.spmv(x)
+        assert_y_close(yb, csr, x, "reloaded")
+        assert np.array_equal(ya[np.abs(ya) > 0] != 0, yb[np.abs(ya) > 0] != 0)
+    with open(p, "r+b") as f:
+        f.write(b"XXXX")
+    with pytest.raises(cvr.CvrError):
+        cvr.CvrMatrix.load(p)
+
+
 def test_64bit_row_delimiters_entry(cvr):
     """row_delim64 is the entry for nnz >= 2^31 (config 5 shards); exercise it at a small size."""
     import torch
