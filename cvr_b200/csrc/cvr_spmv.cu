@@ -5,26 +5,32 @@
 // (paper Alg. 4), including the steal-only chunks (split1 == -1) the
 // reference kernel mishandles.
 //
-// Mapping.  The reference gives one chunk to one OpenMP thread whose AVX-512 register
-// holds the 8 SIMD lanes of a step.  Here one WARP owns one chunk and covers 4 steps x 8
-// lanes = 32 consecutive CVR elements per pass ("window"): thread t of the warp holds
-// element 32k + t, i.e. step 4k + (t >> 3), SIMD lane (t & 7).  vals (8 B) and cols (4 B)
-// are therefore read with fully coalesced 256 B / 128 B warp loads, x is gathered through
-// L1/L2 (ld.global.nc), and each thread keeps a private partial sum for its SIMD lane.
+// Three generations live in this file; all pass the same parity suite and stay selectable
+// (CVR_SPMV_KERNEL = tma | ldg | window) so the choice can be re-measured:
+//   1. cvr_spmv_window_kernel     warp covers 4 consecutive steps, segmented reduction per window
+//                                 (instruction-bound, profiles/r01_v0_*)
+//   2. cvr_spmv_tile_kernel<LDG>  tile walker, operands through the LSU (profiles/r01_v1_*)
+//   3. cvr_spmv_tile_kernel<TMA>  tile walker, operands staged by the TMA engine -- the default
+//                                 (profiles/r01_v3_*); <..., kPublish> additionally pushes finished
+//                                 rows to peer GPUs for the iterated multi-GPU SpMV.
 //
-// Row switches.  A record (pos, wb) means "the accumulator of lane pos%8 is flushed
-// before step pos/8" (spmv.cpp:1197-1210).  The warp holds the next 32 records in
-// registers (one per thread), turns the ones that fall into the current window into a
-// 32-bit flag word with one REDUX.OR, and only then runs a segmented reduction along each
-// SIMD lane (stride-8 shuffles).  Windows without a flag take the fast path: one FMA.
+// Common semantics.  One WARP owns one chunk (the reference: one OpenMP thread).  A record
+// (pos, wb) means "the accumulator of SIMD lane pos%8 is flushed before step pos/8"
+// (spmv.cpp:1197-1210):
 //   feeding record (pos <= split1)  -> y[wb] = sum          plain store, row owned by chunk
 //   stealing record                 -> carry[lane] += sum   (wb == own lane on a first steal)
 //   split0 position                 -> y[first_row] += sum  atomic, row shared with the
 //                                                           previous chunk (spmv.cpp:1280)
 // After the last step the eight pos=-1 records route each lane's remainder into a carry
 // slot (spmv.cpp:1633-1638) and the eight carries are added atomically to y[tail[.]]
-// (spmv.cpp:1640-1649).  y must be zero on entry (the launcher clears it on the same
-// stream, inside the timed region).
+// (spmv.cpp:1640-1649).  The accumulated / never-written rows of y are cleared by
+// cvr_clear_rows_kernel on the same stream, inside the timed region.
+//
+// The first generation, kept below: thread t of the warp holds element 32k + t of window k,
+// i.e. step 4k + (t >> 3), SIMD lane (t & 7); vals / cols are read with coalesced 256 B / 128 B
+// warp loads, x is gathered through L1/L2 (ld.global.nc); the warp holds the next 32 records in
+// registers, turns the ones inside the window into a flag word with one REDUX.OR and runs a
+// segmented reduction along each SIMD lane (stride-8 shuffles); windows without a flag: one FMA.
 #include "cvr_internal.h"
 
 #include <cstdio>

@@ -223,3 +223,27 @@ def test_cli_prints_the_reference_lines(cvr, tmp_path):
     assert any(ln.startswith("The SpMV Execution Time of CVR    is ") for ln in lines)
     assert any(ln.startswith("         The Throughput of CVR    is ") and "GFlops." in ln for ln in lines)
     assert "     Very Good! Your result is correct  " in lines
+
+
+def test_tiny_random_matrices_property(cvr):
+    """Corner cases of the lane scheduler on the device: tiny matrices (fewer than 8 rows, empty rows at
+    chunk starts, rows longer than a chunk) at random legal chunk counts, CUDA vs oracle port."""
+    from test_oracle_property import build_csr
+    rng = np.random.default_rng(2026)
+    for case in range(60):
+        n_rows = int(rng.integers(1, 40))
+        kind = rng.integers(0, 3, n_rows)
+        lens = np.where(kind == 0, 0, np.where(kind == 1, rng.integers(0, 4, n_rows), rng.integers(0, 41, n_rows)))
+        lens = lens.tolist()
+        if sum(lens) == 0:
+            lens.append(3)
+        if lens[-1] < 2:
+            lens[-1] = 2
+        csr = build_csr(lens, seed=case)
+        T = int(rng.integers(1, csr.nnz // 16 + 1))
+        want = oracle.convert(csr, T, "port", fill_missing_tail=True)
+        x = rng.uniform(-1, 1, csr.n_cols + 1)
+        with cvr.CvrMatrix(host_csr(cvr, csr), T) as m:
+            assert_structure_equal(m.export(), want, f"case {case} lens={lens} T={T}")
+            y, _ = m.spmv(x)
+            assert_y_close(y, csr, x, f"case {case} lens={lens} T={T}")
