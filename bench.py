@@ -401,7 +401,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "shard_balance": ("nnz" if not args.row_weight else f"nnz + {args.row_weight:g} per non-empty row")
                        if world > 1 else None,
                        "l2": "inputs exceed L2 (no flush)" if flush is None else "L2 flushed between steps (384 MB write, untimed)",
-                       "step": "clear accumulated rows + cvr_spmv_kernel" + (
+                       "step": "clear accumulated rows + cvr_spmv_kernel (programmatic dependent launch)" + (
                            (" (publishes y rows into every peer's x over NVLink) + accumulated-rows publish + flag barrier"
                             if publisher is not None else " + NCCL all-gather y->x") if iterated else "")},
             "gpu_launches": int(launches),

@@ -447,6 +447,10 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
         int2 held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
         double lane_carry = 0.0; // open partial sum of SIMD lane l at the tile boundary
         double carry_slot = 0.0; // private share of t_rets[l] (spmv.cpp:1124)
+        // When launched as a programmatic dependent of cvr_clear_rows_kernel everything above (ring
+        // set-up, descriptor and record loads, the first bulk copies) overlapped its tail; y may only
+        // be written once that grid has completed.  No-op for an ordinary launch.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 
         for (int32_t tile = 0; tile < n_tiles; tile++) {
             const int32_t ts = tile * TILE;
@@ -610,6 +614,9 @@ __global__ void cvr_clear_rows_kernel(double* __restrict__ y, const int32_t* __r
                                       int32_t n_boundary, const int32_t* __restrict__ empty, int32_t n_empty,
                                       bool skip_row0)
 {
+    // programmatic dependent launch: the sweep kernel behind us may start its prologue right away; it
+    // waits (griddepcontrol.wait) for this grid to complete before it touches y
+    asm volatile("griddepcontrol.launch_dependents;");
     const int32_t n = n_boundary + n_empty;
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int32_t row = i < n_boundary ? boundary[i] : empty[i - n_boundary];
@@ -743,6 +750,7 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
     int launched = 0;
     const SpmvKernel k = selected_kernel();
     const int32_t n_clear = rows.n_boundary + rows.n_empty;
+    bool after_clear_kernel = false;
     if (y_is_clear) {
         // the previous iteration's epilogue kernel already cleared the accumulated rows
     } else if (rows.boundary && k != SpmvKernel::Window) {
@@ -750,6 +758,7 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
         cvr_clear_rows_kernel<<<cb < 1184 ? (cb < 1 ? 1 : cb) : 1184, 256, 0, stream>>>(
             y, rows.boundary, rows.n_boundary, rows.empty, rows.n_empty, publish && (publish->mode & 4));
         launched++;
+        after_clear_kernel = true;
     } else if (cudaMemsetAsync(y, 0, sizeof(double) * (size_t)(n_rows + 1), stream) != cudaSuccess) {
         return -1;
     }
@@ -781,9 +790,25 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
         if (pub)
             cvr_spmv_tile_kernel<true, TB_TMA, true><<<pblocks, threads, Geo<TB_TMA>::DYN_SMEM, stream>>>(
                 chunks, n_chunks, vals, cols, record, x, y, *publish);
-        else
-            cvr_spmv_tile_kernel<true, TB_TMA, false><<<pblocks, threads, Geo<TB_TMA>::DYN_SMEM, stream>>>(
-                chunks, n_chunks, vals, cols, record, x, y, none);
+        else {
+            // ordinary SpMV: launch the sweep as a programmatic dependent of the clearing kernel
+            static const bool use_pdl = [] {
+                const char* e = getenv("CVR_NO_PDL");
+                return !(e && *e == '1');
+            }();
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(pblocks);
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = Geo<TB_TMA>::DYN_SMEM;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = (use_pdl && after_clear_kernel && !ev_begin) ? 1 : 0;
+            cudaLaunchKernelEx(&cfg, cvr_spmv_tile_kernel<true, TB_TMA, false>, chunks, n_chunks, vals, cols,
+                               record, x, y, none);
+        }
     }
     launched++;
     if (ev_end) cudaEventRecord(ev_end, stream);
