@@ -317,9 +317,11 @@ int cvr_auto_chunks(int64_t nnz, int device, int32_t* n_chunks)
         return fail(CVR_ERR_CUDA, "cannot query device %d: no CPU fallback", device);
     // One warp per chunk, chunks are nnz-balanced: size the count in whole WAVES of resident
     // warps (SMs x warps the SpMV kernel keeps resident per SM) so the last wave is full, and
-    // aim at ~2K elements (24 KB of stream) per chunk so the fixed per-chunk cost (15 records,
-    // 9 atomics, descriptor) stays small.
-    int64_t target_nnz = 2048;
+    // aim at ~4K elements (48 KB of stream) per chunk: the per-chunk prologue (descriptor -> records ->
+    // first bulk copy, a chain of dependent loads) costs ~2 us of a warp, measured as FEM 69.7 us at
+    // 14208 chunks vs 64.1-64.8 us at 3552-7104; skewed matrices want more, smaller chunks for balance
+    // (R-MAT-22: 322 us at 21312 chunks vs 346 us at 7104), 4K is the compromise.  CVR_CHUNK_NNZ overrides.
+    int64_t target_nnz = 4096;
     if (const char* s = getenv("CVR_CHUNK_NNZ")) {
         const long long v = atoll(s);
         if (v >= 16) target_nnz = v;
