@@ -37,9 +37,11 @@ METRIC = "spmv_gflops"
 UNIT = "GFLOP/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE cvr_spmv_kernel launch, from the committed
-# `ncu --set full` captures of this very command (profiles/r01_v3_tma_<workload>_ncu.csv)
-NCU_DRAM_TRAFFIC = {"fem": 338.48e6 + 6.82e6, "rmat24": 4015.77e6 + 84.02e6,
+# `ncu --set full` captures of this very command (NCU_TRAFFIC_SOURCE)
+NCU_DRAM_TRAFFIC = {"fem": 336.50e6 + 4.35e6, "rmat24": 4015.77e6 + 84.02e6,
                     "web": 69.51e6 + 2.26e6, "road": 1097.91e6 + 165.75e6}
+NCU_TRAFFIC_SOURCE = {"fem": "profiles/r01_final_tma_fem_ncu.csv", "rmat24": "profiles/r01_v3_tma_rmat24_ncu.csv",
+                      "web": "profiles/r01_v3_tma_web_ncu.csv", "road": "profiles/r01_v3_tma_road_ncu.csv"}
 
 
 def measured_peaks():
@@ -410,8 +412,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": NCU_DRAM_TRAFFIC.get(args.workload) if world == 1 else None,
-                         "traffic_source": "profiles/r01_v3_tma_%s_ncu.csv" % args.workload
-                         if (world == 1 and args.workload in NCU_DRAM_TRAFFIC) else None,
+                         "traffic_source": NCU_TRAFFIC_SOURCE.get(args.workload) if world == 1 else None,
                          "peak_source": peak_src,
                          "kernel": "cvr_spmv_kernel", "kernel_us": kernel_s * 1e6,
                          "algorithmic_bytes_per_launch": info["algorithmic_bytes"],
