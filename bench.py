@@ -210,8 +210,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # rank 0 must print exactly one JSON line on stdout: keep NCCL's version banner out of it
-        os.environ["NCCL_DEBUG"] = os.environ.get("CVR_NCCL_DEBUG", "WARN")
+        # rank 0 must print exactly one JSON line on stdout: NCCL writes its version banner (any
+        # NCCL_DEBUG level >= VERSION) and debug lines to stdout unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import cvr_b200
