@@ -117,7 +117,11 @@ cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int
 
     int32_t i = 0;
     while (i < n_steps) {
-        // ---- events of step i: every lane whose counter is 0, in lane order (:814-816)
+        // ---- events of step i: every lane whose counter is 0, in lane order (:814-816).
+        // Every loop over the 8 lanes is unrolled and the one dynamic index (the steal victim) goes
+        // through select chains, so the trackers stay in registers (as local-memory arrays an event
+        // cost ~1.4 us of dependent L1 round trips).
+#pragma unroll
         for (int l = 0; l < CVR_W; l++) {
             if (left[l] != 0) continue;
             const int32_t pos = i * CVR_W + l;
@@ -129,14 +133,17 @@ cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int
                     rec[n_rec++] = make_int2(pos, row[l]);
                 }
                 while (rd[next_row + 1] == rd[next_row]) next_row++; // skip empty rows
-                src[l] = (int32_t)((int64_t)rd[next_row] - s);
+                const int64_t a0 = (int64_t)rd[next_row], a1 = (int64_t)rd[next_row + 1];
+                src[l] = (int32_t)(a0 - s);
                 row[l] = (int32_t)next_row;
-                left[l] = (int32_t)(rd[next_row + 1] - rd[next_row]);
+                left[l] = (int32_t)(a1 - a0);
                 if (next_row == r1) {
                     if (split1 == 0) split1 = pos;
-                    left[l] = (int32_t)(e - (int64_t)rd[next_row]);
+                    left[l] = (int32_t)(e - a0);
+#pragma unroll
                     for (int q = 0; q < CVR_W; q++) tail[q] = row[q];
                     tail_stored = true;
+#pragma unroll
                     for (int q = 0; q < CVR_W; q++)
                         if (left[q] == 0) from[q] = 0; // :855-856
                 }
@@ -144,13 +151,17 @@ cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int
             } else {
                 // stealing (:869-943): split the first lane that holds more than the average
                 int32_t total = 0;
+#pragma unroll
                 for (int q = 0; q < CVR_W; q++) total += left[q];
                 const int32_t ave = total / CVR_W;
-                int victim = 0;
-                while (victim < CVR_W - 1 && !(left[victim] > ave)) victim++;
+                int victim = CVR_W - 1;
+#pragma unroll
+                for (int q = CVR_W - 2; q >= 0; q--)
+                    if (left[q] > ave) victim = q;
                 if (!((stolen >> l) & 1u)) {
                     if (!stealing) {
                         if (split1 == 0) split1 = (span <= CVR_W) ? -1 : pos;
+#pragma unroll
                         for (int q = 0; q < CVR_W; q++) tail[q] = row[q];
                         tail_stored = true;
                         stealing = true;
@@ -160,17 +171,26 @@ cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int
                 } else {
                     rec[n_rec++] = make_int2(pos, from[l]); // :904-909, unreachable (SURVEY 8a-R2 note i)
                 }
+                int32_t vsrc = src[0];
+#pragma unroll
+                for (int q = 1; q < CVR_W; q++) vsrc = (victim == q) ? src[q] : vsrc;
                 from[l] = victim;
-                src[l] = src[victim];
+                src[l] = vsrc;
                 row[l] = victim;
                 left[l] = ave;
-                left[victim] -= ave;
-                src[victim] += ave;
+#pragma unroll
+                for (int q = 0; q < CVR_W; q++) {
+                    if (q == victim) { // (never lane l itself: a stealer holds exactly the average)
+                        left[q] -= ave;
+                        src[q] += ave;
+                    }
+                }
                 dirty |= 1u << victim;
             }
             dirty |= 1u << l;
         }
         // ---- one segment entry per lane that changed its source at this step
+#pragma unroll
         for (int l = 0; l < CVR_W; l++)
             if ((dirty >> l) & 1u) seg[n_seg++] = make_int2(i * CVR_W + l, src[l]);
         dirty = 0;
@@ -189,12 +209,15 @@ cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int
     }
 
     // the eight terminators written inside the last step (:982-999)
+#pragma unroll
     for (int l = 0; l < CVR_W; l++) rec[n_rec + l] = make_int2(-1, from[l] == -1 ? l : from[l]);
     // The reference leaves final_2 unwritten when a chunk never fed its last row nor stole
     // (span <= 8 and all lanes end together); its kernel then reads garbage.  Store the
     // intended rows instead.
-    if (!tail_stored)
+    if (!tail_stored) {
+#pragma unroll
         for (int q = 0; q < CVR_W; q++) tail[q] = row[q];
+    }
 
     CvrChunk c;
     c.start = s;
