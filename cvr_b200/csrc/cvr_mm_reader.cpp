@@ -25,6 +25,9 @@
 #include "../../include/cvr_b200.h"
 
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -123,49 +126,101 @@ extern "C" int cvr_read_matrix_market(const char* path, int flags, cvr_host_csr_
     if (n_rows > 0x7ffffff0LL || n_cols > 0x7ffffff0LL)
         return cvr_set_error(CVR_ERR_RANGE, "matrix dimensions must fit int32");
 
-    // ---- entries (:411-451)
-    std::vector<Entry> ent;
-    ent.reserve((size_t)(symmetric ? 2 * declared : declared) + 16);
+    // ---- entries (:411-451).  The region is cut at newline boundaries into one piece per host thread;
+    // every piece is tokenised independently (mirrored entries inserted right behind their originals, as
+    // the reference does), then the pieces are concatenated in file order.  `pattern` values depend on the
+    // running entry index including mirrors (:417) and are filled in after the concatenation.
     bool dropped_last = false;
-    while (p < end) {
-        eol = (const char*)memchr(p, '\n', (size_t)(end - p));
-        if (!eol) {
-            if (!(flags & CVR_MM_KEEP_LAST_LINE)) { // the reference's eof() loop never sees it
-                dropped_last = skip_space(p, end) < end;
-                break;
-            }
-            eol = end;
+    const char* region_end = end;
+    if (p < end && end[-1] != '\n') { // unterminated last line
+        const char* last_nl = end;
+        while (last_nl > p && last_nl[-1] != '\n') last_nl--;
+        if (!(flags & CVR_MM_KEEP_LAST_LINE)) { // the reference's eof() loop never sees it
+            dropped_last = skip_space(last_nl, end) < end;
+            region_end = last_nl;
         }
-        const char* q = skip_space(p, eol);
-        if (q < eol && *q != '%') {
-            long long r = 0, c = 0;
-            bool okr, okc;
-            q = parse_int(q, eol, &r, &okr);
-            q = parse_int(q, eol, &c, &okc);
-            if (!okr || !okc || r < 1 || r > n_rows || c < 1 || c > n_cols)
-                return cvr_set_error(CVR_ERR_INVALID, "bad entry at byte %lld of %s",
-                                     (long long)(p - buf.data()), path);
-            Entry e;
-            e.row = (int32_t)r;
-            e.col = (int32_t)c;
-            if (pattern) {
-                e.val = (float)(ent.size() % 13);
-            } else {
-                q = skip_space(q, eol);
-                e.val = q < eol ? strtof(q, nullptr) : 0.0f; // real part for `complex`
+    }
+    int n_parts = 1;
+#ifdef _OPENMP
+    n_parts = omp_get_max_threads();
+#endif
+    if (region_end - p < (1 << 20)) n_parts = 1; // small files: not worth a team
+    std::vector<const char*> cut((size_t)n_parts + 1, region_end);
+    cut[0] = p;
+    for (int k = 1; k < n_parts; k++) {
+        const char* q = p + (region_end - p) / n_parts * k;
+        if (q < cut[(size_t)k - 1]) q = cut[(size_t)k - 1];
+        while (q < region_end && q[-1] != '\n') q++; // q > p here, so q[-1] is inside the buffer
+        cut[(size_t)k] = q;
+    }
+    std::vector<std::vector<Entry>> parts((size_t)n_parts);
+    std::vector<long long> bad_at((size_t)n_parts, -1);
+    std::vector<int> bad_kind((size_t)n_parts, 0);
+#pragma omp parallel for schedule(static, 1) num_threads(n_parts)
+    for (int k = 0; k < n_parts; k++) {
+        std::vector<Entry>& out_k = parts[(size_t)k];
+        const char* q0 = cut[(size_t)k];
+        const char* q1 = cut[(size_t)k + 1];
+        out_k.reserve((size_t)((q1 - q0) / 12 + 16) * (symmetric ? 2 : 1));
+        const char* lp = q0;
+        while (lp < q1) {
+            const char* le = (const char*)memchr(lp, '\n', (size_t)(q1 - lp));
+            if (!le) le = q1; // only the kept unterminated last line
+            const char* q = skip_space(lp, le);
+            if (q < le && *q != '%') {
+                long long r = 0, c = 0;
+                bool okr, okc;
+                q = parse_int(q, le, &r, &okr);
+                q = parse_int(q, le, &c, &okc);
+                if (!okr || !okc || r < 1 || r > n_rows || c < 1 || c > n_cols) {
+                    bad_at[(size_t)k] = (long long)(lp - buf.data());
+                    bad_kind[(size_t)k] = 1;
+                    break;
+                }
+                Entry e;
+                e.row = (int32_t)r;
+                e.col = (int32_t)c;
+                e.val = 0.0f;
+                if (!pattern) {
+                    q = skip_space(q, le);
+                    e.val = q < le ? strtof(q, nullptr) : 0.0f; // real part for `complex`
+                }
+                out_k.push_back(e);
+                if (symmetric && e.row != e.col) {
+                    Entry m;
+                    m.row = e.col;
+                    m.col = e.row;
+                    m.val = pattern ? -1.0f : e.val; // pattern: marker, resolved after the concatenation
+                    if (m.row > n_rows || m.col > n_cols) {
+                        bad_at[(size_t)k] = (long long)(lp - buf.data());
+                        bad_kind[(size_t)k] = 2;
+                        break;
+                    }
+                    out_k.push_back(m);
+                }
             }
-            ent.push_back(e);
-            if (symmetric && e.row != e.col) {
-                Entry m;
-                m.row = e.col;
-                m.col = e.row;
-                m.val = e.val;
-                if (m.row > n_rows || m.col > n_cols)
-                    return cvr_set_error(CVR_ERR_INVALID, "symmetric entry outside the matrix in %s", path);
-                ent.push_back(m);
-            }
+            lp = (le < q1) ? le + 1 : q1;
         }
-        p = (eol < end) ? eol + 1 : end;
+    }
+    for (int k = 0; k < n_parts; k++) {
+        if (bad_kind[(size_t)k] == 1)
+            return cvr_set_error(CVR_ERR_INVALID, "bad entry at byte %lld of %s", bad_at[(size_t)k], path);
+        if (bad_kind[(size_t)k] == 2)
+            return cvr_set_error(CVR_ERR_INVALID, "symmetric entry outside the matrix in %s", path);
+    }
+    std::vector<Entry> ent;
+    {
+        size_t total = 0;
+        for (const auto& v : parts) total += v.size();
+        ent.reserve(total + 16);
+        for (auto& v : parts) {
+            ent.insert(ent.end(), v.begin(), v.end());
+            std::vector<Entry>().swap(v);
+        }
+    }
+    if (pattern) { // value = running index % 13; a mirrored entry (marked -1 above) copies its original (:417, :447)
+        for (size_t k = 0; k < ent.size(); k++)
+            ent[k].val = (ent[k].val < 0.0f && k > 0) ? ent[k - 1].val : (float)(k % 13);
     }
     if (dropped_last)
         fprintf(stderr, "cvr: %s does not end with a newline; its last line is dropped like the "

@@ -129,3 +129,32 @@ def test_invalid_chunk_counts():
     _, csr = load_golden("fem6")
     with pytest.raises(ValueError):
         oracle.convert(csr, csr.nnz // 16 + 1, "port")
+
+
+@pytest.mark.parametrize("kind", ["real_general", "pattern_symmetric"])
+def test_parallel_ingest_of_a_large_file_matches_the_oracle(kind, native_lib, tmp_path):
+    """Files above 1 MB are tokenised by several host threads (cvr_mm_reader.cpp); the result must not
+    depend on where the pieces were cut -- compare with the reference's readMatrix when it is available,
+    with the port otherwise."""
+    import cvr_b200
+    rng = np.random.default_rng(17)
+    n, m = 50000, 160000
+    r = rng.integers(1, n + 1, m)
+    c = rng.integers(1, n + 1, m)
+    p = str(tmp_path / f"{kind}.mtx")
+    with open(p, "w") as f:
+        if kind == "real_general":
+            v = rng.uniform(-1, 1, m).astype(np.float32)
+            f.write("%%MatrixMarket matrix coordinate real general\n% comment\n" + f"{n} {n} {m}\n")
+            np.savetxt(f, np.column_stack([r, c, v]), fmt="%d %d %.9g")
+        else:
+            f.write("%%MatrixMarket matrix coordinate pattern symmetric\n" + f"{n} {n} {m}\n")
+            np.savetxt(f, np.column_stack([r, c]), fmt="%d %d")
+    assert os.path.getsize(p) > (1 << 20)
+    got = cvr_b200.read_matrix(p, ref_last_delim=True)
+    want = oracle.read_mtx(p, "ref" if oracle.ref_available() else "port", ref_last_delim=True) \
+        if not oracle.ref_available() else oracle.read_mtx(p, "ref")
+    assert [got.n_rows, got.n_cols, got.nnz] == [want.n_rows, want.n_cols, want.nnz]
+    np.testing.assert_array_equal(got.col, want.col)
+    np.testing.assert_array_equal(got.val, want.val)
+    np.testing.assert_array_equal(got.row_delim, want.row_delim)
