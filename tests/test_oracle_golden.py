@@ -152,8 +152,7 @@ def test_parallel_ingest_of_a_large_file_matches_the_oracle(kind, native_lib, tm
             np.savetxt(f, np.column_stack([r, c]), fmt="%d %d")
     assert os.path.getsize(p) > (1 << 20)
     got = cvr_b200.read_matrix(p, ref_last_delim=True)
-    want = oracle.read_mtx(p, "ref" if oracle.ref_available() else "port", ref_last_delim=True) \
-        if not oracle.ref_available() else oracle.read_mtx(p, "ref")
+    want = oracle.read_mtx(p, "ref") if oracle.ref_available() else oracle.read_mtx(p, "port", ref_last_delim=True)
     assert [got.n_rows, got.n_cols, got.nnz] == [want.n_rows, want.n_cols, want.nnz]
     np.testing.assert_array_equal(got.col, want.col)
     np.testing.assert_array_equal(got.val, want.val)
