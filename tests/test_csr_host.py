@@ -1,0 +1,38 @@
+"""CPU suite: host-side CSR helpers (the conventions of readMatrix) and the writer/reader round trip."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def test_from_coo_follows_readmatrix_conventions(native_lib):
+    import cvr_b200
+    rows = np.array([3, 1, 3, 2, 1])
+    cols = np.array([2, 4, 1, 2, 1])
+    vals = np.array([0.1, 0.2, 0.3, 0.4, 0.5])
+    m = cvr_b200.CsrMatrix.from_coo(rows, cols, vals, 3, 4)
+    assert m.nnz == 16 and m.nnz_true == 5                      # padded to a multiple of 16 (spmv.cpp:457)
+    assert m.row_delim.tolist() == [0, 0, 13, 14, 16]           # pads are copies of the LAST given entry (1,1)
+    assert m.col[:13].tolist() == [1] * 12 + [4]                # (1,1) x12 (1 real + 11 zero pads), then (1,4)
+    assert np.count_nonzero(m.val) == 5
+    assert m.val.dtype == np.float64 and np.all(m.val == m.val.astype(np.float32))  # float32-rounded (spmv.cpp:65)
+    with pytest.raises(ValueError):
+        cvr_b200.CsrMatrix(3, 4, m.val[:15], m.col[:15], m.row_delim)
+
+
+def test_write_mtx_then_read_matrix_round_trip(native_lib, tmp_path):
+    import cvr_b200
+    from cvr_b200 import gen
+    d = gen.random_sparse(400, 300, 2500, seed=33, empty_frac=0.2).to_host()
+    rows = d.row_of_entry()
+    p = str(tmp_path / "rt.mtx")
+    cvr_b200.write_mtx(p, d.n_rows, d.n_cols, rows, d.col, d.val)   # padding zeros included as explicit entries
+    back = cvr_b200.read_matrix(p)
+    assert [back.n_rows, back.n_cols, back.nnz] == [d.n_rows, d.n_cols, d.nnz]
+    np.testing.assert_array_equal(back.col, d.col)
+    np.testing.assert_array_equal(back.val, d.val)
+    np.testing.assert_array_equal(back.row_delim, d.row_delim)
+    # and the oracle's reader agrees with the product's on the same file
+    port = oracle.read_mtx(p, "port")
+    np.testing.assert_array_equal(port.col, back.col)
+    np.testing.assert_array_equal(port.row_delim, back.row_delim)
