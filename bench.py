@@ -38,10 +38,9 @@ UNIT = "GFLOP/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE cvr_spmv_kernel launch, from the committed
 # `ncu --set full` captures of this very command (NCU_TRAFFIC_SOURCE)
-NCU_DRAM_TRAFFIC = {"fem": 336.50e6 + 4.35e6, "rmat24": 4015.77e6 + 84.02e6,
-                    "web": 69.51e6 + 2.26e6, "road": 1097.91e6 + 165.75e6}
-NCU_TRAFFIC_SOURCE = {"fem": "profiles/r01_final_tma_fem_ncu.csv", "rmat24": "profiles/r01_v3_tma_rmat24_ncu.csv",
-                      "web": "profiles/r01_v3_tma_web_ncu.csv", "road": "profiles/r01_v3_tma_road_ncu.csv"}
+NCU_DRAM_TRAFFIC = {"fem": 336.50e6 + 4.35e6, "rmat24": 3952.51e6 + 85.03e6,
+                    "web": 69.51e6 + 3.22e6, "road": 1094.03e6 + 167.53e6}
+NCU_TRAFFIC_SOURCE = {w: "profiles/r01_final_tma_%s_ncu.csv" % w for w in NCU_DRAM_TRAFFIC}
 
 
 def measured_peaks():
