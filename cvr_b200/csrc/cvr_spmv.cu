@@ -638,6 +638,10 @@ __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_
                                             int32_t n_empty, const __grid_constant__ CvrPublish pub,
                                             const __grid_constant__ CvrBarrier bar, unsigned int* done_counter)
 {
+    // the next iteration's sweep may start its prologue (descriptors, records, first bulk copies of the
+    // matrix stream) while this kernel publishes and waits at the barrier; it does not touch x or y
+    // before its griddepcontrol.wait, i.e. before this grid -- barrier included -- has completed
+    asm volatile("griddepcontrol.launch_dependents;");
     const bool publish_empty = (pub.mode & 2) == 0;
     const bool aliased = (pub.mode & 4) != 0;
     double* next_y = pub.clear_next ? pub.clear_next : y;
@@ -787,10 +791,26 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
             cvr_spmv_tile_kernel<false, TB_LDG, false><<<pblocks, threads, 0, stream>>>(
                 chunks, n_chunks, vals, cols, record, x, y, none);
     } else {
-        if (pub)
-            cvr_spmv_tile_kernel<true, TB_TMA, true><<<pblocks, threads, Geo<TB_TMA>::DYN_SMEM, stream>>>(
-                chunks, n_chunks, vals, cols, record, x, y, *publish);
-        else {
+        if (pub) {
+            // iterated SpMV: from the second iteration on the kernel in front of us is the previous
+            // iteration's epilogue (publish + barrier): launch as its programmatic dependent
+            static const bool use_pdl_pub = [] {
+                const char* e = getenv("CVR_NO_PDL");
+                return !(e && *e == '1');
+            }();
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(pblocks);
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = Geo<TB_TMA>::DYN_SMEM;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = (use_pdl_pub && (y_is_clear || after_clear_kernel) && !ev_begin) ? 1 : 0;
+            cudaLaunchKernelEx(&cfg, cvr_spmv_tile_kernel<true, TB_TMA, true>, chunks, n_chunks, vals, cols, record,
+                               x, y, *publish);
+        } else {
             // ordinary SpMV: launch the sweep as a programmatic dependent of the clearing kernel
             static const bool use_pdl = [] {
                 const char* e = getenv("CVR_NO_PDL");
