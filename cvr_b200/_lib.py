@@ -76,6 +76,7 @@ SIGNATURES = {
     "cvr_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "cvr_get_info": (C.c_int, [C.c_void_p, C.POINTER(CvrInfo)]),
     "cvr_device_vectors": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "cvr_device_arrays": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cvr_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "cvr_get_kernel_timing": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),
     "cvr_destroy": (None, [C.c_void_p]),

@@ -504,6 +504,16 @@ int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev)
     return CVR_OK;
 }
 
+int cvr_device_arrays(cvr_handle_t* h, const double** vals_dev, const int32_t** cols_dev,
+                      const int32_t** record_dev)
+{
+    if (!h) return fail(CVR_ERR_INVALID, "NULL handle");
+    if (vals_dev) *vals_dev = h->vals;
+    if (cols_dev) *cols_dev = h->cols;
+    if (record_dev) *record_dev = h->record;
+    return CVR_OK;
+}
+
 int cvr_set_kernel_timing(cvr_handle_t* h, int enabled)
 {
     if (!h) return fail(CVR_ERR_INVALID, "NULL handle");

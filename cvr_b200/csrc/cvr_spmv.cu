@@ -709,13 +709,10 @@ SpmvKernel selected_kernel()
 {
     // CVR_SPMV_KERNEL = tma (default) | ldg | window: the earlier generations stay selectable so
     // that the choice can be re-measured (profiles/ holds the ncu captures of each)
-    static const SpmvKernel k = [] {
-        const char* e = getenv("CVR_SPMV_KERNEL");
-        if (e && strcmp(e, "window") == 0) return SpmvKernel::Window;
-        if (e && strcmp(e, "ldg") == 0) return SpmvKernel::Ldg;
-        return SpmvKernel::Tma;
-    }();
-    return k;
+    const char* e = getenv("CVR_SPMV_KERNEL"); // read per call: tools/kernel_ab.py switches it at run time
+    if (e && strcmp(e, "window") == 0) return SpmvKernel::Window;
+    if (e && strcmp(e, "ldg") == 0) return SpmvKernel::Ldg;
+    return SpmvKernel::Tma;
 }
 
 } // namespace
@@ -769,8 +766,8 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
     const int threads = WARPS * 32;
     const int blocks = (int)(((int64_t)n_chunks * 32 + threads - 1) / threads);
     // the tile kernels are persistent: one block per resident slot, warps stride over the chunks
-    static int resident_blocks = 0;
-    if (resident_blocks == 0) {
+    int resident_blocks = 0;
+    {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

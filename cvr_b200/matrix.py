@@ -127,6 +127,12 @@ class CvrMatrix:
         _lib.check(self._lib.cvr_device_vectors(self._h, C.byref(x), C.byref(y)))
         return x.value, y.value
 
+    def device_arrays(self):
+        """Raw device addresses (vals, cols, record) of the converted matrix, for measurement tools."""
+        v, c, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(self._lib.cvr_device_arrays(self._h, C.byref(v), C.byref(c), C.byref(r)))
+        return v.value, c.value, r.value
+
     # -- the hot path
     def spmv(self, x, iters: int = 1):
         """spmv_compute_kernel with host vectors: returns (y[n_rows+1], seconds per iteration).

@@ -204,6 +204,12 @@ int cvr_get_info(cvr_handle_t* h, cvr_info_t* info);
  * doubles), for callers that iterate on the device. */
 int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev);
 
+/* Device pointers of the converted matrix itself (read-only views, valid until cvr_destroy):
+ * vals [nnz] f64, cols [nnz] i32 in CVR order, record [record_ints] i32.  For tools that run their
+ * own kernels over the CVR arrays (tools/probe, tools/compare.py); any out-pointer may be NULL. */
+int cvr_device_arrays(cvr_handle_t* h, const double** vals_dev, const int32_t** cols_dev,
+                      const int32_t** record_dev);
+
 /* Measurement aid: while enabled, every SpMV launch is bracketed by a CUDA event pair on
  * its stream (after y has been cleared), so the SpMV kernel's own device time can be
  * reported next to the whole-step time.  cvr_get_kernel_timing waits for the recorded
