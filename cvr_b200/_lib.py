@@ -36,7 +36,8 @@ class CvrInfo(C.Structure):  # cvr_info_t
 
 
 class CvrPublish(C.Structure):  # cvr_publish_t
-    _fields_ = [("n_dst", C.c_int32), ("mode", C.c_int32), ("row_offset", C.c_int64), ("needs", C.c_void_p),
+    _fields_ = [("n_dst", C.c_int32), ("self", C.c_int32), ("mode", C.c_int32), ("row_offset", C.c_int64),
+                ("needs", C.c_void_p),
                 ("chunk_any", C.c_void_p), ("clear_next", C.c_void_p), ("dst", C.c_void_p * 8)]
 
 
@@ -64,6 +65,7 @@ SIGNATURES = {
     "cvr_spmv_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvr_spmv_publish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CvrPublish), C.POINTER(C.c_void_p),
                                   C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]),
+    "cvr_check_async_error": (C.c_int, [C.c_void_p]),
     "cvr_column_footprint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvr_chunk_needs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvr_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
@@ -71,6 +73,8 @@ SIGNATURES = {
     "cvr_peer_close": (C.c_int, [C.c_int, C.c_void_p]),
     "cvr_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
     "cvr_peer_barrier": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
+    "cvr_verify_csr": (C.c_int, [C.POINTER(CvrCsr), C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
+                                c_int64_p, c_double_p, c_int64_p]),
     "cvr_export": (C.c_int, [C.c_void_p, C.POINTER(CvrArrays)]),
     "cvr_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "cvr_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
@@ -103,7 +107,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError = ABI drift, fail loudly
             fn.restype = res
             fn.argtypes = args
-        if lib.cvr_abi_version() != 1:
+        if lib.cvr_abi_version() != 2:
             raise RuntimeError("libcvr_b200 ABI version mismatch")
         _lib = lib
     return _lib

@@ -16,7 +16,7 @@ BIN_DIR = os.path.join(PKG, "bin")
 LIB = os.path.join(LIB_DIR, "libcvr_b200.so")
 CLI = os.path.join(BIN_DIR, "spmv.cvr")
 
-CUDA_SOURCES = ["cvr_api.cu", "cvr_convert.cu", "cvr_spmv.cu", "cvr_mm_reader.cpp"]
+CUDA_SOURCES = ["cvr_api.cu", "cvr_convert.cu", "cvr_spmv.cu", "cvr_check.cu", "cvr_mm_reader.cpp"]
 CLI_SOURCES = ["cli/spmv_cvr_main.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

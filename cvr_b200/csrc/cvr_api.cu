@@ -34,6 +34,19 @@ namespace {
                         __FILE__, __LINE__);                                                \
     } while (0)
 
+// bound of the peer-barrier spin: CVR_BARRIER_TIMEOUT_MS (default 3000) in SM clocks of `device`
+long long barrier_timeout_cycles(int device)
+{
+    long long ms = 3000;
+    if (const char* e = getenv("CVR_BARRIER_TIMEOUT_MS")) {
+        const long long v = atoll(e);
+        if (v > 0) ms = v;
+    }
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) != cudaSuccess || khz <= 0) khz = 1965000;
+    return ms * (long long)khz;
+}
+
 double wall_seconds()
 {
     using namespace std::chrono;
@@ -64,7 +77,8 @@ struct cvr_handle {
     int64_t device_bytes = 0;
     std::vector<CvrChunk> host_chunks; // copy of the descriptors (export / info)
     // optional per-launch timing of the SpMV kernel alone (cvr_set_kernel_timing)
-    unsigned int* done_counter = nullptr; // last-block detection of the publish epilogue
+    unsigned int* done_counter = nullptr; // [0] last-block detection of the publish epilogue,
+                                          // [1] epoch of the first peer barrier that timed out (0 = none)
     bool timing = false;
     std::vector<cudaEvent_t> timing_events; // begin/end pairs, `timing_used` of them recorded
     size_t timing_used = 0;
@@ -372,15 +386,20 @@ int cvr_spmv_publish(cvr_handle_t* h, const double* x_dev, double* y_dev, const 
     b.rank = rank;
     b.n_ranks = n_ranks;
     b.epoch = epoch;
+    b.timeout_cycles = barrier_timeout_cycles(h->device);
     if (!h->done_counter) {
         CUDA_TRY(cudaSetDevice(h->device));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->done_counter), sizeof(unsigned int)));
-        CUDA_TRY(cudaMemset(h->done_counter, 0, sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->done_counter), 2 * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(h->done_counter, 0, 2 * sizeof(unsigned int)));
     }
+    b.error = h->done_counter + 1;
     if (pub->n_dst < 1 || pub->n_dst > CVR_MAX_PEERS)
         return fail(CVR_ERR_INVALID, "n_dst = %d must be in [1, %d]", pub->n_dst, CVR_MAX_PEERS);
+    if ((pub->mode & 4) && (pub->self < 0 || pub->self >= pub->n_dst))
+        return fail(CVR_ERR_INVALID, "mode bit 2 needs self = %d in [0, n_dst)", pub->self);
     CvrPublish p{};
     p.n_dst = pub->n_dst;
+    p.self = pub->self;
     p.mode = pub->mode;
     p.row_offset = pub->row_offset;
     p.needs = pub->needs;
@@ -411,7 +430,7 @@ static int spmv_device_impl(cvr_handle_t* h, const double* x_dev, double* y_dev,
         ee = h->timing_events[h->timing_used + 1];
         h->timing_used += 2;
     }
-    const int launched = cvr_launch_spmv(h->chunks, h->n_chunks, h->vals, h->cols, h->record,
+    const int launched = cvr_launch_spmv(h->chunks, h->n_chunks, h->nnz, h->vals, h->cols, h->record,
                                          x_dev, y_dev, h->n_rows, h->rows, pub,
                                          static_cast<cudaStream_t>(cuda_stream), eb, ee, bar,
                                          h->done_counter, y_is_clear);
@@ -539,6 +558,22 @@ int cvr_get_kernel_timing(cvr_handle_t* h, double* total_seconds, int64_t* launc
     return CVR_OK;
 }
 
+int cvr_check_async_error(cvr_handle_t* h)
+{
+    if (!h) return fail(CVR_ERR_INVALID, "NULL handle");
+    if (!h->done_counter) return CVR_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned int epoch = 0;
+    CUDA_TRY(cudaMemcpy(&epoch, h->done_counter + 1, sizeof(epoch), cudaMemcpyDeviceToHost));
+    if (epoch != 0) {
+        CUDA_TRY(cudaMemset(h->done_counter + 1, 0, sizeof(unsigned int)));
+        return fail(CVR_ERR_STATE,
+                    "peer flag barrier timed out at epoch %u (a peer stalled; CVR_BARRIER_TIMEOUT_MS): the x "
+                    "vectors of this and later iterations are not trustworthy", epoch);
+    }
+    return CVR_OK;
+}
+
 int cvr_column_footprint(cvr_handle_t* h, uint8_t* used_dev, void* cuda_stream)
 {
     if (!h || !used_dev) return fail(CVR_ERR_INVALID, "NULL argument");
@@ -611,6 +646,8 @@ int cvr_peer_barrier(int device, void* const* flag_arrays, int32_t rank, int32_t
     b.rank = rank;
     b.n_ranks = n_ranks;
     b.epoch = epoch;
+    b.error = nullptr;
+    b.timeout_cycles = barrier_timeout_cycles(device);
     if (cvr_launch_peer_barrier(b, static_cast<cudaStream_t>(cuda_stream)) < 0)
         return fail(CVR_ERR_CUDA, "barrier launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return CVR_OK;

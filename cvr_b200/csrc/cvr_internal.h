@@ -44,6 +44,7 @@ __host__ __device__ inline int64_t cvr_segment_offset(int64_t chunk, int64_t fir
 // the x vectors of this GPU and of its peers (peer-mapped device pointers).  Passed by value.
 struct CvrPublish {
     int32_t n_dst;                 // 0: do not publish
+    int32_t self;                  // index of THIS GPU's own buffer in dst[] (used with mode bit 2)
     int32_t mode;                  // bit 0: per-row stores at emit instead of the coalesced per-chunk push (A/B)
                                    // bit 1: do not re-publish 0.0 for the never-written rows
                                    // bit 2: y IS this GPU's slice of the next x (no local copy; y[0] is foreign)
@@ -59,6 +60,8 @@ struct CvrBarrier {
     uint32_t* flags[CVR_MAX_PEERS]; // flags[p]: rank p's flag array (n_ranks words), peer-mapped
     int32_t rank, n_ranks;
     uint32_t epoch;
+    unsigned int* error;     // device word: set to the epoch of the first barrier that timed out (0 = none)
+    long long timeout_cycles; // bound of the spin in SM clocks
 };
 
 struct CvrConvertArgs {
@@ -95,7 +98,7 @@ int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t*
 // Launchers (each returns the number of kernels it launched, or <0 on launch failure)
 int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream);
 // ev_begin / ev_end (optional) bracket the SpMV kernel alone, after y has been cleared
-int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals,
+int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, int64_t nnz, const double* vals,
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
                     int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
                     cudaStream_t stream, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr,
@@ -110,6 +113,8 @@ int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used,
 
 // resident warps per SM of the SpMV kernel in use (sizes the automatic chunk count)
 int cvr_spmv_resident_warps_per_sm();
+// name of the sweep variant CVR_SPMV_KERNEL selects ("pipe9x4", "tile", ...)
+const char* cvr_spmv_kernel_name();
 
 // force-load the kernels' module so the first timed call does not pay CUDA's lazy loading
 void cvr_preload_convert_kernels();

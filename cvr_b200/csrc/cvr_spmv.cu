@@ -5,14 +5,18 @@
 // (paper Alg. 4), including the steal-only chunks (split1 == -1) the
 // reference kernel mishandles.
 //
-// Three generations live in this file; all pass the same parity suite and stay selectable
-// (CVR_SPMV_KERNEL = tma | ldg | window) so the choice can be re-measured:
-//   1. cvr_spmv_window_kernel     warp covers 4 consecutive steps, segmented reduction per window
-//                                 (instruction-bound, profiles/r01_v0_*)
-//   2. cvr_spmv_tile_kernel<LDG>  tile walker, operands through the LSU (profiles/r01_v1_*)
-//   3. cvr_spmv_tile_kernel<TMA>  tile walker, operands staged by the TMA engine -- the default
-//                                 (profiles/r01_v3_*); <..., kPublish> additionally pushes finished
-//                                 rows to peer GPUs for the iterated multi-GPU SpMV.
+// Two sweep kernels live in this file (CVR_SPMV_KERNEL = pipe | tile selects one per launch; both
+// pass the same parity suite, tests/test_gpu_parity.py runs it over both):
+//   cvr_spmv_tile_kernel   round 1: tile walker, vals/cols staged by the TMA engine, one tile in flight
+//                          per warp (profiles/r01_*)
+//   cvr_spmv_pipe_kernel   round 2, the default: the same walker, software-pipelined -- the x gathers
+//                          of tile k+1 are in flight while tile k is walked, the TMA ring runs two
+//                          tiles ahead and crosses chunk boundaries, record batches are prefetched
+//                          (profiles/r02_*).  <..., kPublish> variants additionally push finished
+//                          rows to peer GPUs for the iterated multi-GPU SpMV.
+// The first two generations of round 1 (a window kernel with a warp-wide segmented reduction and the
+// walker with LDG-streamed operands) were re-measured against these on B200 (profiles/
+// r02_kernel_ab_round1_generations.jsonl: never faster on any workload) and removed.
 //
 // Common semantics.  One WARP owns one chunk (the reference: one OpenMP thread).  A record
 // (pos, wb) means "the accumulator of SIMD lane pos%8 is flushed before step pos/8"
@@ -25,12 +29,6 @@
 // slot (spmv.cpp:1633-1638) and the eight carries are added atomically to y[tail[.]]
 // (spmv.cpp:1640-1649).  The accumulated / never-written rows of y are cleared by
 // cvr_clear_rows_kernel on the same stream, inside the timed region.
-//
-// The first generation, kept below: thread t of the warp holds element 32k + t of window k,
-// i.e. step 4k + (t >> 3), SIMD lane (t & 7); vals / cols are read with coalesced 256 B / 128 B
-// warp loads, x is gathered through L1/L2 (ld.global.nc); the warp holds the next 32 records in
-// registers, turns the ones inside the window into a flag word with one REDUX.OR and runs a
-// segmented reduction along each SIMD lane (stride-8 shuffles); windows without a flag: one FMA.
 #include "cvr_internal.h"
 
 #include <cstdio>
@@ -40,196 +38,27 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int UNROLL = 4; // windows whose loads are in flight together
-
-__device__ __forceinline__ double ld_stream_f64(const double* p)
-{
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int32_t ld_stream_s32(const int32_t* p)
-{
-    int32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
-struct WarpState {
-    double acc;   // private partial sum of my SIMD lane since its last flush
-    double carry; // private share of t_rets[my lane] (spmv.cpp:1124)
-    int2 held;    // record rb + t
-    int32_t rb, rc; // record batch base / records consumed
-    int32_t last_pos;
-};
-
-// Segmented flush of one window that contains at least one flag.
-__device__ __forceinline__ void flush_window(WarpState& st, const int2* __restrict__ rec,
-                                             int32_t n_rec, double prod, unsigned rflags,
-                                             unsigned flags, int32_t wstart, int t,
-                                             int32_t split0, int32_t split1, int32_t first_row,
-                                             const int32_t* __restrict__ tail,
-                                             double* __restrict__ y)
-{
-    const int j = t >> 3, l = t & 7;
-    // lane totals of the private partial sums
-    double tot = st.acc + __shfl_xor_sync(FULL, st.acc, 8);
-    tot += __shfl_xor_sync(FULL, tot, 16);
-    // products of the up-to-three earlier steps of my SIMD lane inside this window
-    const double q1 = __shfl_up_sync(FULL, prod, 8);
-    const double q2 = __shfl_up_sync(FULL, prod, 16);
-    const double q3 = __shfl_up_sync(FULL, prod, 24);
-    // my record, if my position is flagged by one
-    const int rank = __popc(rflags & ((1u << t) - 1u));
-    const int32_t wb = __shfl_sync(FULL, st.held.y, (st.rc - st.rb + rank) & 31);
-
-    const unsigned lane_bits = flags & (0x01010101u << l);
-    if (lane_bits == 0) {
-        st.acc += prod;
-    } else {
-        if ((flags >> t) & 1u) {
-            // sum of the segment that ends right before my step
-            double e = 0.0;
-            bool open = true;
-            if (j >= 1) { e += q1; open = !((flags >> (t - 8)) & 1u); }
-            if (j >= 2 && open) { e += q2; open = !((flags >> (t - 16)) & 1u); }
-            if (j >= 3 && open) { e += q3; open = !((flags >> (t - 24)) & 1u); }
-            if (open) e += tot;
-            const int32_t pos = wstart + t;
-            if ((rflags >> t) & 1u) {
-                if (split1 != -1 && pos <= split1) y[wb] = e; // feeding: exclusive row
-                else if (wb == l) st.carry += e;               // stealing: a first steal names its own lane
-                else if (tail[wb] != 0) atomicAdd(&y[tail[wb]], e); // (second steal, unreachable: SURVEY 8a-R2 note i)
-            } else {
-                atomicAdd(&y[first_row], e);                   // split0: shared first row
-            }
-        }
-        // elements at or after the lane's last flag open the next segment
-        st.acc = ((lane_bits >> t) >> 1) ? 0.0 : prod;
-    }
-    st.rc += __popc(rflags);
-    (void)rec; (void)n_rec; (void)split0;
-}
-
-__global__ void __launch_bounds__(128)
-cvr_spmv_window_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
-                const double* __restrict__ vals, const int32_t* __restrict__ cols,
-                const int32_t* __restrict__ record, const double* __restrict__ x,
-                double* __restrict__ y)
-{
-    const int32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (chunk >= T) return;
-    const int t = threadIdx.x & 31;
-
-    // chunk descriptor: one 64 B line, every thread reads the same words (broadcast loads)
-    const CvrChunk* cp = chunks + chunk;
-    const int64_t start = cp->start;
-    const int32_t len = cp->len;
-    const int32_t first_row = cp->first_row;
-    const int32_t split0 = cp->split0;
-    const int32_t split1 = cp->split1;
-    const int32_t n_rec = cp->n_rec;
-
-    const int2* rec = reinterpret_cast<const int2*>(record + cvr_record_offset(chunk, first_row));
-    const double* v = vals + start;
-    const int32_t* c = cols + start;
-
-    WarpState st;
-    st.acc = 0.0;
-    st.carry = 0.0;
-    st.rb = st.rc = 0;
-    st.held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
-    st.last_pos = __shfl_sync(FULL, st.held.x, 31);
-
-    const int32_t n_win = (len + CVR_WIN - 1) / CVR_WIN;
-    for (int32_t k0 = 0; k0 < n_win; k0 += UNROLL) {
-        double a[UNROLL], xv[UNROLL];
-        int32_t ci[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const int32_t p = (k0 + u) * CVR_WIN + t;
-            const bool in = p < len;
-            a[u] = in ? ld_stream_f64(v + p) : 0.0;
-            ci[u] = in ? ld_stream_s32(c + p) : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) xv[u] = __ldg(x + ci[u]);
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const int32_t k = k0 + u;
-            if (k < n_win) { // warp-uniform
-                const int32_t wstart = k * CVR_WIN;
-                if (st.rc != st.rb && (uint32_t)st.last_pos < (uint32_t)(wstart + CVR_WIN)) {
-                    st.rb = st.rc; // batch may not cover this window: reload from the cursor
-                    st.held = (st.rb + t < n_rec) ? rec[st.rb + t] : make_int2(-1, 0);
-                    st.last_pos = __shfl_sync(FULL, st.held.x, 31);
-                }
-                const unsigned rel = (unsigned)(st.held.x - wstart);
-                const unsigned rflags = __reduce_or_sync(FULL, rel < 32u ? (1u << rel) : 0u);
-                const unsigned s0rel = (unsigned)(split0 - wstart);
-                const unsigned flags = rflags | ((split0 != 0 && s0rel < 32u) ? (1u << s0rel) : 0u);
-                if (flags == 0) {
-                    st.acc = fma(a[u], xv[u], st.acc);
-                } else {
-                    flush_window(st, rec, n_rec, a[u] * xv[u], rflags, flags, wstart, t, split0,
-                                 split1, first_row, cp->tail, y);
-                }
-            }
-        }
-    }
-
-    // ---- chunk epilogue: lane remainders through the eight pos=-1 records
-    double tot = st.acc + __shfl_xor_sync(FULL, st.acc, 8);
-    tot += __shfl_xor_sync(FULL, tot, 16);          // every thread: total of SIMD lane (t & 7)
-    double carry = st.carry + __shfl_xor_sync(FULL, st.carry, 8);
-    carry += __shfl_xor_sync(FULL, carry, 16);      // every thread: carry slot (t & 7)
-    const int32_t term_wb = (t < CVR_W) ? rec[n_rec + t].y : 0;
-#pragma unroll
-    for (int l = 0; l < CVR_W; l++) {
-        const double r = __shfl_sync(FULL, tot, l);
-        const int32_t w = __shfl_sync(FULL, term_wb, l);
-        if (t == w) carry += r;                     // t_rets[wb] += lane l (spmv.cpp:1637)
-    }
-    if (t < CVR_W) {
-        const int32_t row = cp->tail[t];
-        // row 0 is the phantom row unused lanes point at (their carry is 0.0): skipping it
-        // avoids n_chunks atomics on one address
-        if (row != 0) atomicAdd(&y[row], carry);    // spmv.cpp:1647-1648
-    }
-}
-
 
 // ---------------------------------------------------------------------------------------
-// Tile walker (the default kernel).
+// Tile walker.
 //
-// ncu on the window kernel above (profiles/r01_v0_*) showed it instruction-bound: with ~27
-// nnz per row some lane switches rows in 3 of 4 windows, so nearly every window paid the
-// warp-wide segmented reduction (82 warp-instructions per 32 nnz, 43 % issue utilisation,
-// 2.1 TB/s).  Here a warp still owns one chunk, but a pass covers a TILE of 32 steps x 8
-// lanes and thread t = (q, l) walks TB CONSECUTIVE steps of SIMD lane l:
-// steps TB*q .. TB*q+TB-1 of the tile.  A row switch is then a thread-local event (emit the
-// accumulator, clear it); threads of the same SIMD lane only meet once per tile, in a
-// 3-shuffle carry chain that hands the open partial sum from walker q to walker q+1.
-//   * loads: for each of the 8 steps a warp load touches 4 x 64 B (vals) / 4 x 32 B (cols)
-//     fully used sectors; all 16 loads of a tile are issued before the first use.
+// A warp owns one chunk at a time; a pass covers a TILE of 4*TB steps x 8 lanes and thread
+// t = (q, l) walks TB CONSECUTIVE steps of SIMD lane l: steps TB*q .. TB*q+TB-1 of the tile.
+// A row switch is then a thread-local event (emit the accumulator, clear it); threads of the same
+// SIMD lane only meet once per tile, in a 3-shuffle carry chain that hands the open partial sum
+// from walker q to walker q+1.
+//   * the vals/cols stream never passes the LSU: per tile ONE lane arms an mbarrier and issues two
+//     cp.async.bulk copies (global -> shared, L2 evict-first); the walkers read their operands from
+//     the stage with conflict-free 64-bit / 32-bit shared loads (see TB below).
 //   * records are delivered to their owner thread through shared memory: the warp holds 32
 //     records in registers (coalesced 256 B load), each holder drops a flag byte and the
 //     write-back target into the owner's slot.
-//   * kTma = true (default): the vals/cols stream does not go through the LSU at all.  ncu on
-//     the LDG variant (profiles/r01_v1_*) shows the L1TEX data pipe as the busiest unit
-//     (57-74 % of its wavefront peak): every x gather costs one wavefront per distinct line,
-//     so the streamed operands are moved by the TMA engine instead: per tile one lane arms an
-//     mbarrier and eight lanes issue cp.async.bulk (global -> shared, L2 evict-first), two
-//     stages deep, i.e. the copy of tile k+1/k+2 overlaps the gather + FMA walk of tile k.
-//     Each walker's quarter of the tile lands in its own padded slot so that the 64-bit
-//     shared loads of the four walkers fall on disjoint banks.
 // ---------------------------------------------------------------------------------------
-// TB (consecutive steps per walker) is 9 for the TMA variant, ODD on purpose: a walker's
-// quarter of the tile is then 9 x 64 B = 576 B of vals and 288 B of cols, so the four walkers
-// start 16 (vals) / 8 (cols) shared-memory banks apart and their 64-bit / 32-bit loads of one
-// step are conflict-free in the plain linear layout ONE bulk copy per array produces.  (With
-// TB = 8 the quarters alias on the same banks; padding each quarter separately needed 8 small
-// copies per tile.)  The LDG variant has no such constraint and uses TB = 8.
+// TB (consecutive steps per walker) is ODD on purpose: a walker's quarter of the tile is then
+// TB x 64 B of vals and TB x 32 B of cols, so the four walkers start 16 (vals) / 8 (cols)
+// shared-memory banks apart and their 64-bit / 32-bit loads of one step are conflict-free in the
+// plain linear layout ONE bulk copy per array produces.  (With TB = 8 the quarters alias on the
+// same banks; padding each quarter separately needed 8 small copies per tile.)
 constexpr int WARPS = 4;              // warps per block
 constexpr int32_t WB_SPLIT0 = -2;     // marker: flush into the shared first row
 constexpr int32_t PUSH_MAX_ROWS = 1024; // widest row range a warp publishes as one contiguous push
@@ -257,6 +86,16 @@ struct TileCtx {
     int l;
 };
 
+// Destinations of one published row: the footprint bits when the exchange is sparse, otherwise
+// every destination -- EXCEPT this GPU's own buffer when y already IS its slice of the next x
+// (mode bit 2): re-storing a stale copy of y[r] over itself would race with the neighbouring
+// chunks' atomicAdds on shared rows.
+__device__ __forceinline__ uint32_t publish_mask(const CvrPublish& pub, int32_t row)
+{
+    if (pub.needs) return pub.needs[row];
+    return (pub.mode & 4) ? (0xffu & ~(1u << pub.self)) : 0xffu;
+}
+
 // A finished row that this chunk owns alone: one plain store (spmv.cpp:1204).
 template <bool kPublish>
 __device__ __forceinline__ void store_row(const TileCtx& cx, int32_t row, double value)
@@ -264,7 +103,7 @@ __device__ __forceinline__ void store_row(const TileCtx& cx, int32_t row, double
     cx.y[row] = value;
     if (kPublish && cx.scatter) { // scattered 8-byte peer stores, row by row
         const int64_t g = cx.pub->row_offset + row;
-        const uint32_t nb = cx.pub->needs ? cx.pub->needs[row] : 0xffu;
+        const uint32_t nb = publish_mask(*cx.pub, row);
 #pragma unroll
         for (int p = 0; p < CVR_MAX_PEERS; p++)
             if (p < cx.pub->n_dst && ((nb >> p) & 1u)) cx.pub->dst[p][g] = value;
@@ -291,7 +130,7 @@ __device__ __forceinline__ void publish_chunk_rows(const TileCtx& cx, int32_t fi
         for (int u = 0; u < 4; u++) {
             const bool in = r0 + 32 * u <= last_row;
             v[u] = in ? __ldcg(cx.y + r0 + 32 * u) : 0.0;
-            nb[u] = !in ? 0u : (pub.needs ? pub.needs[r0 + 32 * u] : 0xffu);
+            nb[u] = !in ? 0u : publish_mask(pub, r0 + 32 * u);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -355,15 +194,12 @@ __device__ __forceinline__ void fma_if(double& acc, double a, double x, uint32_t
 // flag bytes (0/1) of a 32-bit word -> 4-bit mask
 __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return ((w * 0x00204081u) >> 21) & 0xfu; }
 
-#ifndef CVR_LDG_BLOCKS
-#define CVR_LDG_BLOCKS 8
-#endif
 #ifndef CVR_TMA_BLOCKS
 #define CVR_TMA_BLOCKS 6
 #endif
 
-template <bool kTma, int TB, bool kPublish>
-__global__ void __launch_bounds__(WARPS * 32, kTma ? CVR_TMA_BLOCKS : CVR_LDG_BLOCKS)
+template <int TB, bool kPublish>
+__global__ void __launch_bounds__(WARPS * 32, CVR_TMA_BLOCKS)
 cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
                      const double* __restrict__ vals, const int32_t* __restrict__ cols,
                      const int32_t* __restrict__ record, const double* __restrict__ x,
@@ -374,7 +210,7 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
     __shared__ uint32_t s_flags[WARPS][FLAG_WORDS][32]; // one flag byte per (thread, step)
     __shared__ int32_t s_wb[WARPS][TB][32];             // write-back target per (step, thread)
     __shared__ __align__(8) unsigned long long s_bar[WARPS][STAGES];
-    extern __shared__ __align__(128) unsigned char s_stream[]; // kTma: WARPS x STAGES tiles
+    extern __shared__ __align__(128) unsigned char s_stream[]; // WARPS x STAGES tiles
 
     const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = t >> 3, l = t & 7;
@@ -383,17 +219,18 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
 
     // ---- per-warp TMA ring, set up once: the warp is persistent and walks chunks
     // warp0, warp0 + n_warps, ... (chunks are nnz-balanced, so a static round robin is even)
-    const uint32_t ring = kTma ? smem_u32(s_stream + w * G::WARP_SMEM) : 0u;
-    const uint32_t bar0 = kTma ? smem_u32(&s_bar[w][0]) : 0u;
+    // iterated multi-GPU SpMV: the publish epilogue behind us is a programmatic dependent; let its
+    // blocks become resident as ours retire (it waits for this grid to complete before it reads y)
+    if (kPublish) asm volatile("griddepcontrol.launch_dependents;");
+    const uint32_t ring = smem_u32(s_stream + w * G::WARP_SMEM);
+    const uint32_t bar0 = smem_u32(&s_bar[w][0]);
     uint64_t policy = 0;
     uint32_t n_issued = 0, n_waited = 0; // tiles issued to / consumed from the ring, all chunks
-    if (kTma) {
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-        if (t == 0) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (t == 0) {
 #pragma unroll
-            for (int sidx = 0; sidx < STAGES; sidx++) mbar_init(bar0 + 8u * sidx, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+        for (int sidx = 0; sidx < STAGES; sidx++) mbar_init(bar0 + 8u * sidx, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 #pragma unroll
     for (int k = 0; k < FLAG_WORDS; k++) s_flags[w][k][t] = 0u;
@@ -437,11 +274,9 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
             }
             n_issued++;
         };
-        if (kTma) {
 #pragma unroll
-            for (int sidx = 0; sidx < STAGES; sidx++)
-                if (sidx < n_tiles) issue_tile(sidx);
-        }
+        for (int sidx = 0; sidx < STAGES; sidx++)
+            if (sidx < n_tiles) issue_tile(sidx);
 
         int32_t rb = 0;
         int2 held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
@@ -459,7 +294,7 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
 
             double a[TB], xv[TB];
             uint32_t ci[TB];
-            if (kTma) {
+            {
                 const uint32_t sidx = n_waited % STAGES;
                 mbar_wait(bar0 + 8u * sidx, (n_waited / STAGES) & 1u);
                 n_waited++;
@@ -486,23 +321,6 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (tile + STAGES < n_tiles) issue_tile(tile + STAGES);
-            } else {
-                const double* gv = v + p0;
-                const uint32_t* gc = reinterpret_cast<const uint32_t*>(c) + p0;
-                if (full) {
-#pragma unroll
-                    for (int b = 0; b < TB; b++) {
-                        a[b] = ld_stream_f64(gv + b * CVR_W);
-                        ci[b] = (uint32_t)ld_stream_s32(reinterpret_cast<const int32_t*>(gc + b * CVR_W));
-                    }
-                } else {
-#pragma unroll
-                    for (int b = 0; b < TB; b++) {
-                        const bool in = p0 + b * CVR_W < len;
-                        a[b] = in ? ld_stream_f64(gv + b * CVR_W) : 0.0;
-                        ci[b] = in ? (uint32_t)ld_stream_s32(reinterpret_cast<const int32_t*>(gc + b * CVR_W)) : 0u;
-                    }
-                }
             }
 #pragma unroll
             for (int b = 0; b < TB; b++) xv[b] = __ldg(x + ci[b]);
@@ -601,11 +419,314 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
     }
 }
 
-#ifndef CVR_TB_TMA
-#define CVR_TB_TMA 9
-#endif
-constexpr int TB_TMA = CVR_TB_TMA, TB_LDG = 8;
-static_assert(TB_TMA % 2 == 1, "the TMA tile needs an odd number of steps per walker (bank layout)");
+
+// ---------------------------------------------------------------------------------------
+// cvr_spmv_pipe_kernel -- the walker above, software-pipelined (round 2, the default).
+//
+// Why: tools/probe (profiles/r02_gather_probe_summary.txt) shows that on matrices whose x gather
+// misses L1 (R-MAT, web) one SM retires at most ~1 gathered element per clock however many warps or
+// loads are in flight -- the L1 miss path, not HBM, is the ceiling (R-MAT-24: 0.94 ms for "stream +
+// gather + FMA" against 1.40 ms for the round-1 sweep).  The round-1 sweep loses the difference in
+// DUTY CYCLE: a warp issues the 288 gathers of a tile, waits for them, and only then delivers
+// records, walks, emits and synchronises -- all of that with no gather of its own outstanding.
+// Here the warp keeps the miss path fed from one tile to the next:
+//   * the x gathers of tile g+1 are issued BEFORE tile g is walked (xv / xv_next registers);
+//   * the TMA ring is two stages deep and runs two tiles ahead; the fetch side needs no
+//     descriptor (chunk start / length are closed-form in (chunk, nnz, T), spmv.cpp:584-627), so it
+//     crosses chunk boundaries: the first tiles of the warp's next chunk are already in flight
+//     while the current chunk's tail is walked and its epilogue runs;
+//   * record batches are prefetched one batch (32 records) ahead, so the delivery loop does not
+//     wait on a dependent global load per batch.
+// Per tile g (stage s = g & 1):
+//   1. wait full[s^1]; read cols of tile g+1 from the stage; issue its gathers -> xv_next
+//   2. read vals of tile g (its barrier was waited for one iteration earlier)
+//   3. fence.proxy.async + syncwarp; lane 0 re-arms stage s with tile g+2
+//   4. deliver records, walk, carry chain, emits of tile g (chunk prologue / epilogue around it)
+//   5. xv <- xv_next
+// ---------------------------------------------------------------------------------------
+template <int TB>
+struct PipeGeo {
+    static constexpr int TILE = 4 * TB * CVR_W;
+    static constexpr int QUARTER = TB * CVR_W;
+    static constexpr int FLAG_WORDS = (TB + 3) / 4;
+    static constexpr int STAGE_BYTES = TILE * 12;        // vals then cols
+    static constexpr int WARP_SMEM = 2 * STAGE_BYTES;    // two stages per warp
+    static constexpr int DYN_SMEM = WARPS * WARP_SMEM;
+};
+
+template <int TB, int NB, bool kPublish>
+__global__ void __launch_bounds__(WARPS * 32, NB)
+cvr_spmv_pipe_kernel(const CvrChunk* __restrict__ chunks, int32_t T, int64_t nnz,
+                     const double* __restrict__ vals, const int32_t* __restrict__ cols,
+                     const int32_t* __restrict__ record, const double* __restrict__ x,
+                     double* __restrict__ y, const __grid_constant__ CvrPublish pub)
+{
+    using G = PipeGeo<TB>;
+    constexpr int TILE = G::TILE, QUARTER = G::QUARTER, FLAG_WORDS = G::FLAG_WORDS;
+    __shared__ uint32_t s_flags[WARPS][FLAG_WORDS][32]; // one flag byte per (thread, step)
+    __shared__ int32_t s_wb[WARPS][TB][32];             // write-back target per (step, thread)
+    __shared__ __align__(8) unsigned long long s_bar[WARPS][2];
+    extern __shared__ __align__(128) unsigned char s_stream[]; // WARPS x 2 stages
+
+    const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = t >> 3, l = t & 7;
+    const int32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    // iterated multi-GPU SpMV: the publish epilogue behind us is a programmatic dependent; let its
+    // blocks become resident as ours retire (it waits for this grid to complete before it reads y)
+    if (kPublish) asm volatile("griddepcontrol.launch_dependents;");
+    if (warp0 >= T) return; // no chunk for this warp (never with the launcher's grid)
+
+    const uint32_t ring = smem_u32(s_stream + w * G::WARP_SMEM);
+    const uint32_t bar0 = smem_u32(&s_bar[w][0]);
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (t == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#pragma unroll
+    for (int k = 0; k < FLAG_WORDS; k++) s_flags[w][k][t] = 0u;
+    __syncwarp();
+
+    // ---- fetch side: the warp's tile sequence (chunks warp0, warp0 + n_warps, ...; every tile of each)
+    // in closed form -- nnz-balanced slices in multiples of 16 (spmv.cpp:584-586, :615-627)
+    const int64_t per = (nnz / T / 16) * 16;
+    const int64_t brk = (nnz - per * T) / 16;
+    int32_t f_chunk = warp0, f_tile = 0, f_ntiles = 0, f_len = 0;
+    int64_t f_start = 0;
+    auto fetch_enter = [&](int32_t c) {
+        f_chunk = c;
+        f_tile = 0;
+        if (c < T) {
+            f_start = c < brk ? c * (per + 16) : c * per + brk * 16;
+            f_len = (int32_t)(c == T - 1 ? nnz - f_start : (c < brk ? per + 16 : per));
+            f_ntiles = (f_len + TILE - 1) / TILE;
+        }
+    };
+    // start the bulk copies of the next tile of the sequence into stage `sidx`; returns its element
+    // count (0: the sequence is exhausted)
+    auto fetch_issue = [&](uint32_t sidx) -> int32_t {
+        if (f_chunk >= T) return 0;
+        const int32_t ts = f_tile * TILE;
+        const int32_t n_el = min(TILE, f_len - ts); // multiple of 16
+        if (t == 0) {
+            const uint32_t bar = bar0 + 8u * sidx;
+            const uint32_t stage = ring + sidx * G::STAGE_BYTES;
+            mbar_expect_tx(bar, (uint32_t)n_el * 12u);
+            bulk_g2s(stage, vals + f_start + ts, (uint32_t)n_el * 8u, bar, policy);
+            bulk_g2s(stage + TILE * 8, cols + f_start + ts, (uint32_t)n_el * 4u, bar, policy);
+        }
+        if (++f_tile == f_ntiles) fetch_enter(f_chunk + n_warps);
+        return n_el;
+    };
+    fetch_enter(warp0);
+    int32_t nel0 = fetch_issue(0); // tile being walked
+    int32_t nel1 = fetch_issue(1); // tile whose gathers are in flight
+    int32_t nel2 = 0;              // tile just issued to the ring
+
+    // cols of a tile -> gathers of x (columns of elements past the chunk end read the phantom x[0])
+    auto gather_tile = [&](uint32_t sidx, int32_t n_el, double (&out)[TB]) {
+        const uint32_t* sc =
+            reinterpret_cast<const uint32_t*>(s_stream + w * G::WARP_SMEM + sidx * G::STAGE_BYTES + TILE * 8) +
+            q * QUARTER + l;
+        uint32_t ci[TB];
+        if (n_el == TILE) {
+#pragma unroll
+            for (int b = 0; b < TB; b++) ci[b] = sc[b * CVR_W];
+        } else {
+#pragma unroll
+            for (int b = 0; b < TB; b++) ci[b] = (q * QUARTER + l + b * CVR_W < n_el) ? sc[b * CVR_W] : 0u;
+        }
+#pragma unroll
+        for (int b = 0; b < TB; b++) out[b] = __ldg(x + ci[b]);
+    };
+
+    // ---- walk side: per-chunk state
+    int32_t chunk = warp0, w_tile = 0, w_ntiles = 1;
+    const CvrChunk* cp = chunks + chunk;
+    int32_t split0 = 0, n_rec = 0, chunk_last_row = 0;
+    const int2* rec = nullptr;
+    int32_t rb = 0;
+    int2 held = make_int2(-1, 0), nxt = make_int2(-1, 0);
+    double lane_carry = 0.0, carry_slot = 0.0;
+    TileCtx cx;
+    cx.y = y;
+    cx.pub = &pub;
+    cx.l = l;
+    cx.tail = cp->tail;
+    cx.scatter = false;
+    cx.split1 = 0;
+    cx.first_row = 0;
+
+    // When launched as a programmatic dependent (of the clearing kernel, or of the previous iteration's
+    // publish epilogue) everything above overlapped the predecessor's tail; x may only be read and y
+    // written once that grid has completed.  No-op for an ordinary launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    double xv[TB], xv_next[TB];
+    mbar_wait(bar0, 0u);
+    gather_tile(0u, nel0, xv);
+
+    for (uint32_t g = 0;; g++) {
+        const uint32_t sidx = g & 1u;
+        // ---- 0. chunk prologue: descriptor and the first two record batches (their latency overlaps
+        // the barrier wait and the gathers below)
+        if (w_tile == 0) {
+            cp = chunks + chunk;
+            const int32_t len = cp->len;
+            split0 = cp->split0;
+            n_rec = cp->n_rec;
+            chunk_last_row = cp->last_row;
+            cx.tail = cp->tail;
+            cx.split1 = cp->split1;
+            cx.first_row = cp->first_row;
+            // A chunk in a very sparse region can span 10^5 (mostly empty) rows: pushing that range from
+            // one warp would serialise; such chunks publish their few finished rows one by one instead
+            cx.scatter = kPublish && ((pub.mode & 1) || chunk_last_row - cx.first_row >= PUSH_MAX_ROWS);
+            w_ntiles = (len + TILE - 1) / TILE;
+            rec = reinterpret_cast<const int2*>(record + cvr_record_offset(chunk, cx.first_row));
+            rb = 0;
+            held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
+            nxt = (32 + t < n_rec) ? rec[32 + t] : make_int2(-1, 0);
+            lane_carry = 0.0;
+            carry_slot = 0.0;
+        }
+        // ---- 1. gathers of tile g+1
+        if (nel1 > 0) {
+            mbar_wait(bar0 + 8u * (sidx ^ 1u), ((g + 1u) >> 1) & 1u);
+            gather_tile(sidx ^ 1u, nel1, xv_next);
+        }
+        // ---- 2. vals of tile g
+        const int32_t ts = w_tile * TILE;
+        const int32_t p0 = ts + q * QUARTER + l; // my element of step TB*q of the tile; next step: +8
+        double a[TB];
+        {
+            const double* sv =
+                reinterpret_cast<const double*>(s_stream + w * G::WARP_SMEM + sidx * G::STAGE_BYTES) + q * QUARTER + l;
+            if (nel0 == TILE) {
+#pragma unroll
+                for (int b = 0; b < TB; b++) a[b] = sv[b * CVR_W];
+            } else {
+#pragma unroll
+                for (int b = 0; b < TB; b++) a[b] = (q * QUARTER + l + b * CVR_W < nel0) ? sv[b * CVR_W] : 0.0;
+            }
+        }
+        // ---- 3. stage `sidx` is free (cols read one iteration ago, vals just now): refill it with tile
+        // g+2.  The refill is an async-proxy write to memory these generic-proxy loads just read:
+        // fence in every reader, converge, then re-arm.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        nel2 = fetch_issue(sidx);
+
+        // ---- 4a. deliver the records of this tile to their owner threads
+        for (;;) {
+            const uint32_t rel = (uint32_t)(held.x - ts);
+            if (rel < (uint32_t)TILE) {
+                const uint32_t step = rel >> 3, wq = step / TB, b = step - wq * TB;
+                const uint32_t owner = wq * CVR_W + (rel & 7u);
+                reinterpret_cast<unsigned char*>(&s_flags[w][b >> 2][owner])[b & 3u] = 1;
+                s_wb[w][b][owner] = held.y;
+            }
+            const int32_t last = __shfl_sync(FULL, held.x, 31);
+            if ((uint32_t)last >= (uint32_t)(ts + TILE)) break; // batch reaches past the tile (or ended)
+            rb += 32;
+            held = nxt;
+            nxt = (rb + 32 + t < n_rec) ? rec[rb + 32 + t] : make_int2(-1, 0);
+        }
+        if (t == 0 && split0 != 0) {
+            const uint32_t rel = (uint32_t)(split0 - ts);
+            if (rel < (uint32_t)TILE) {
+                const uint32_t step = rel >> 3, wq = step / TB, b = step - wq * TB;
+                const uint32_t owner = wq * CVR_W + (rel & 7u);
+                reinterpret_cast<unsigned char*>(&s_flags[w][b >> 2][owner])[b & 3u] = 1;
+                s_wb[w][b][owner] = WB_SPLIT0;
+            }
+        }
+        __syncwarp();
+        uint32_t mask = 0; // bit b: my SIMD lane switches rows before step b of my share
+#pragma unroll
+        for (int k = 0; k < FLAG_WORDS; k++) {
+            const uint32_t fw = s_flags[w][k][t];
+            if (fw) s_flags[w][k][t] = 0u;
+            mask |= bytes_to_bits(fw) << (4 * k);
+        }
+
+        // ---- 4b. walk my TB steps with two predicated FMA chains: `head` collects the steps before my
+        // first flag (everything if I have none), `tail` the steps from my last flag on.
+        const int b_first = mask ? __ffs(mask) - 1 : TB;
+        const int b_last = mask ? 31 - __clz(mask) : TB;
+        const uint32_t below = (1u << b_first) - 1u;        // steps before the first flag
+        const uint32_t after = ~((1u << b_last) - 1u);      // steps from the last flag on
+        double head = 0.0, tailsum = 0.0;
+        const uint32_t after_m = mask ? after : 0u;
+#pragma unroll
+        for (int b = 0; b < TB; b++) {
+            fma_if(head, a[b], xv[b], below & (1u << b));
+            fma_if(tailsum, a[b], xv[b], after_m & (1u << b));
+        }
+        // segments strictly between two flags of the same thread (short rows): emit in place
+        if (b_last > b_first) {
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < TB; b++) {
+                if (b > b_first && ((mask >> b) & 1u)) {
+                    emit<kPublish>(cx, acc, p0 + b * CVR_W, s_wb[w][b][t], carry_slot);
+                    acc = 0.0;
+                }
+                if (b >= b_first && b < b_last) acc = fma(a[b], xv[b], acc);
+            }
+        }
+
+        // ---- 4c. carry chain over the four walkers of my SIMD lane
+        const bool has = mask != 0u;
+        double cin = (q == 0) ? lane_carry : 0.0;
+        double out = has ? tailsum : cin + head;
+#pragma unroll
+        for (int r = 1; r < 4; r++) {
+            const double prev = __shfl_up_sync(FULL, out, CVR_W);
+            if (q == r) {
+                cin = prev;
+                out = has ? tailsum : cin + head;
+            }
+        }
+        lane_carry = __shfl_sync(FULL, out, 24 + l);
+        if (has) emit<kPublish>(cx, head + cin, p0 + b_first * CVR_W, s_wb[w][b_first][t], carry_slot);
+        __syncwarp(); // slots are reused by the next tile's delivery
+
+        // ---- 4d. chunk epilogue: lane remainders through the eight pos=-1 records (spmv.cpp:1633-1649)
+        if (++w_tile == w_ntiles) {
+            double carry = carry_slot + __shfl_xor_sync(FULL, carry_slot, 8);
+            carry += __shfl_xor_sync(FULL, carry, 16);
+            const int32_t term_wb = (t < CVR_W) ? rec[n_rec + t].y : 0;
+#pragma unroll
+            for (int k = 0; k < CVR_W; k++) {
+                const double r = __shfl_sync(FULL, lane_carry, k);
+                const int32_t wbk = __shfl_sync(FULL, term_wb, k);
+                if (t == wbk) carry += r;
+            }
+            if (t < CVR_W) {
+                const int32_t row = cp->tail[t];
+                if (row != 0) atomicAdd(&y[row], carry); // row 0 = phantom row of unused lanes (carry 0.0)
+            }
+            if (kPublish && !cx.scatter && (!pub.chunk_any || pub.chunk_any[chunk]))
+                publish_chunk_rows(cx, cx.first_row, chunk_last_row, t);
+            chunk += n_warps;
+            w_tile = 0;
+        }
+
+        // ---- 5. rotate the pipeline
+        if (nel1 == 0) break;
+#pragma unroll
+        for (int b = 0; b < TB; b++) xv[b] = xv_next[b];
+        nel0 = nel1;
+        nel1 = nel2;
+    }
+}
+
+constexpr int TB_TILE = 9; // round-1 kernel: tile = 288 elements
+static_assert(TB_TILE % 2 == 1, "the TMA tile needs an odd number of steps per walker (bank layout)");
 
 // ---- small helper kernels around the sweep
 // y is cleared only where it is accumulated (boundary rows) or never written (empty rows, row 0):
@@ -625,6 +746,28 @@ __global__ void cvr_clear_rows_kernel(double* __restrict__ y, const int32_t* __r
     }
 }
 
+// All-to-all flag barrier over peer-mapped memory, run by the first n_ranks threads of one block:
+// every rank writes `epoch` into its slot of every rank's flag array (after a system-scope fence,
+// so the rows it published are visible first) and waits until all of its own slots carry the epoch.
+// The spin is bounded (a lost peer must not hang the GPU) -- and a timeout is NOT silent: the epoch
+// is recorded in *b.error, which cvr_check_async_error turns into CVR_ERR_STATE on the host.
+__device__ __forceinline__ void peer_flag_barrier(const CvrBarrier& b, int p)
+{
+    if (p >= b.n_ranks) return;
+    __threadfence_system();
+    volatile uint32_t* remote = b.flags[p] + b.rank;
+    *remote = b.epoch;
+    volatile uint32_t* mine = b.flags[b.rank] + p;
+    const long long t0 = clock64();
+    while ((int32_t)(*mine - b.epoch) < 0) {
+        if (clock64() - t0 > b.timeout_cycles) {
+            if (b.error) atomicCAS(b.error, 0u, b.epoch); // first failing epoch wins
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
 // After the sweep of an iterated multi-GPU SpMV, ONE epilogue kernel does everything that has to
 // wait for the sweep to be complete:
 //   1. the accumulated rows are final now: publish them; rows nothing writes get an explicit 0.0
@@ -633,15 +776,19 @@ __global__ void cvr_clear_rows_kernel(double* __restrict__ y, const int32_t* __r
 //   2. clear those rows of y again, ready for the next sweep (cvr_launch_spmv then skips its own
 //      clearing kernel);
 //   3. the last block to finish runs the all-to-all flag barrier over peer memory.
+// It is launched as a programmatic dependent of the sweep (its blocks are resident and waiting when
+// the sweep's last warp retires -- no launch gap), and the next iteration's sweep as a programmatic
+// dependent of it.
 __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_t* __restrict__ boundary,
                                             int32_t n_boundary, const int32_t* __restrict__ empty,
                                             int32_t n_empty, const __grid_constant__ CvrPublish pub,
                                             const __grid_constant__ CvrBarrier bar, unsigned int* done_counter)
 {
-    // the next iteration's sweep may start its prologue (descriptors, records, first bulk copies of the
+    // the next iteration's sweep may start its prologue (barrier set-up, first bulk copies of the
     // matrix stream) while this kernel publishes and waits at the barrier; it does not touch x or y
     // before its griddepcontrol.wait, i.e. before this grid -- barrier included -- has completed
     asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory"); // the sweep in front of us is complete and visible
     const bool publish_empty = (pub.mode & 2) == 0;
     const bool aliased = (pub.mode & 4) != 0;
     double* next_y = pub.clear_next ? pub.clear_next : y;
@@ -659,12 +806,12 @@ __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_
             next_y[row] = 0.0;
         }
         const int64_t g = pub.row_offset + row;
-        const uint32_t nb = pub.needs ? pub.needs[row] : 0xffu;
+        const uint32_t nb = publish_mask(pub, row);
 #pragma unroll
         for (int p = 0; p < CVR_MAX_PEERS; p++)
             if (p < pub.n_dst && ((nb >> p) & 1u)) pub.dst[p][g] = v;
     }
-    // ---- last block: flag barrier (see cvr_peer_barrier_kernel)
+    // ---- last block: flag barrier
     __shared__ bool is_last;
     __threadfence_system();
     __syncthreads();
@@ -672,47 +819,139 @@ __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_
     __syncthreads();
     if (!is_last) return;
     if (threadIdx.x == 0) *done_counter = 0u;
-    const int p = threadIdx.x;
-    if (p >= bar.n_ranks) return;
-    __threadfence_system();
-    volatile uint32_t* remote = bar.flags[p] + bar.rank;
-    *remote = bar.epoch;
-    volatile uint32_t* mine = bar.flags[bar.rank] + p;
-    const long long t0 = clock64();
-    while ((int32_t)(*mine - bar.epoch) < 0) {
-        if (clock64() - t0 > 6000000000LL) break; // ~3 s: a lost peer must not hang the GPU
-    }
-    __threadfence_system();
+    peer_flag_barrier(bar, threadIdx.x);
 }
 
-// All-to-all flag barrier over peer-mapped memory: every rank writes `epoch` into its slot of every
-// rank's flag array (after a system-scope fence, so the rows it published are visible first) and
-// waits until all of its own slots carry the epoch.  Bounded spin: a lost peer must not hang the GPU.
 __global__ void cvr_peer_barrier_kernel(const __grid_constant__ CvrBarrier b)
 {
-    const int p = threadIdx.x;
-    if (p >= b.n_ranks) return;
-    __threadfence_system();
-    volatile uint32_t* remote = b.flags[p] + b.rank;
-    *remote = b.epoch;
-    volatile uint32_t* mine = b.flags[b.rank] + p;
-    const long long t0 = clock64();
-    while ((int32_t)(*mine - b.epoch) < 0) {
-        if (clock64() - t0 > 6000000000LL) break; // ~3 s
-    }
-    __threadfence_system();
+    peer_flag_barrier(b, threadIdx.x);
 }
 
-enum class SpmvKernel { Tma, Ldg, Window };
+// ---- sweep variants.  `pipeTxB` = cvr_spmv_pipe_kernel<T, B>: T steps per walker (tile = 32 T
+// elements), B resident blocks (4 warps each) per SM requested through __launch_bounds__.
+struct Variant {
+    const char* name;
+    bool pipe;
+    int tb, nb;
+};
+constexpr Variant VARIANTS[] = {
+    {"tile", false, TB_TILE, CVR_TMA_BLOCKS},
+    {"pipe9x4", true, 9, 4},
+    {"pipe9x5", true, 9, 5},
+    {"pipe7x5", true, 7, 5},
+    {"pipe7x6", true, 7, 6},
+    {"pipe5x6", true, 5, 6},
+    {"pipe5x8", true, 5, 8},
+};
+constexpr int N_VARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
+#ifndef CVR_DEFAULT_VARIANT
+#define CVR_DEFAULT_VARIANT 1
+#endif
 
-SpmvKernel selected_kernel()
+int selected_variant()
 {
-    // CVR_SPMV_KERNEL = tma (default) | ldg | window: the earlier generations stay selectable so
-    // that the choice can be re-measured (profiles/ holds the ncu captures of each)
-    const char* e = getenv("CVR_SPMV_KERNEL"); // read per call: tools/kernel_ab.py switches it at run time
-    if (e && strcmp(e, "window") == 0) return SpmvKernel::Window;
-    if (e && strcmp(e, "ldg") == 0) return SpmvKernel::Ldg;
-    return SpmvKernel::Tma;
+    // CVR_SPMV_KERNEL = tile | pipe (= the default) | pipe<T>x<B>; read per call so that
+    // tools/kernel_ab.py and the parity suite can switch it at run time
+    const char* e = getenv("CVR_SPMV_KERNEL");
+    if (!e || !*e || strcmp(e, "pipe") == 0) return CVR_DEFAULT_VARIANT;
+    for (int v = 0; v < N_VARIANTS; v++)
+        if (strcmp(e, VARIANTS[v].name) == 0) return v;
+    return CVR_DEFAULT_VARIANT;
+}
+
+template <typename K, typename... Args>
+cudaError_t launch_ex(K kernel, int blocks, int threads, int smem, cudaStream_t stream, bool programmatic,
+                      Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = programmatic ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// one entry per variant: occupancy query and launch, plain and publishing flavour
+template <int TB, int NB>
+struct PipeOps {
+    static int resident_blocks()
+    {
+        int blocks = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_pipe_kernel<TB, NB, false>, WARPS * 32,
+                                                          PipeGeo<TB>::DYN_SMEM) != cudaSuccess)
+            return 0;
+        return blocks;
+    }
+    static cudaError_t launch(bool publish, int blocks, cudaStream_t stream, bool programmatic,
+                              const CvrChunk* chunks, int32_t T, int64_t nnz, const double* vals,
+                              const int32_t* cols, const int32_t* record, const double* x, double* y,
+                              const CvrPublish& pub)
+    {
+        if (publish)
+            return launch_ex(cvr_spmv_pipe_kernel<TB, NB, true>, blocks, WARPS * 32, PipeGeo<TB>::DYN_SMEM, stream,
+                             programmatic, chunks, T, nnz, vals, cols, record, x, y, pub);
+        return launch_ex(cvr_spmv_pipe_kernel<TB, NB, false>, blocks, WARPS * 32, PipeGeo<TB>::DYN_SMEM, stream,
+                         programmatic, chunks, T, nnz, vals, cols, record, x, y, pub);
+    }
+    static void preload()
+    {
+        cudaFuncAttributes a;
+        cudaFuncGetAttributes(&a, cvr_spmv_pipe_kernel<TB, NB, false>);
+    }
+};
+
+#define CVR_FOR_PIPE_VARIANT(v, expr)                   \
+    switch (v) {                                        \
+    case 1: { using P = PipeOps<9, 4>; expr; } break;   \
+    case 2: { using P = PipeOps<9, 5>; expr; } break;   \
+    case 3: { using P = PipeOps<7, 5>; expr; } break;   \
+    case 4: { using P = PipeOps<7, 6>; expr; } break;   \
+    case 5: { using P = PipeOps<5, 6>; expr; } break;   \
+    case 6: { using P = PipeOps<5, 8>; expr; } break;   \
+    default: break;                                     \
+    }
+
+// resident blocks per SM of a variant on the current device (cached per device and variant)
+int variant_resident_blocks(int v)
+{
+    static int cache[64][N_VARIANTS] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int* slot = (dev >= 0 && dev < 64) ? &cache[dev][v] : nullptr;
+    if (slot && *slot > 0) return *slot;
+    int blocks = 0;
+    if (!VARIANTS[v].pipe) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<TB_TILE, false>, WARPS * 32,
+                                                          Geo<TB_TILE>::DYN_SMEM) != cudaSuccess)
+            blocks = 0;
+    } else {
+        CVR_FOR_PIPE_VARIANT(v, blocks = P::resident_blocks())
+    }
+    if (blocks <= 0) blocks = 4;
+    if (slot) *slot = blocks;
+    return blocks;
+}
+
+int device_sm_count()
+{
+    static int cache[64] = {};
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    if (dev >= 0 && dev < 64) cache[dev] = sms;
+    return sms;
+}
+
+bool pdl_enabled()
+{
+    const char* e = getenv("CVR_NO_PDL");
+    return !(e && *e == '1');
 }
 
 } // namespace
@@ -720,43 +959,42 @@ SpmvKernel selected_kernel()
 void cvr_preload_spmv_kernels()
 {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<true, TB_TMA, false>);
+    const int v = selected_variant();
+    if (!VARIANTS[v].pipe) cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB_TILE, false>);
+    else {
+        CVR_FOR_PIPE_VARIANT(v, P::preload())
+    }
     cudaFuncGetAttributes(&a, cvr_clear_rows_kernel);
 }
 
 // resident warps per SM of the selected kernel (used to size the automatic chunk count)
 int cvr_spmv_resident_warps_per_sm()
 {
-    int blocks = 0;
-    const SpmvKernel k = selected_kernel();
-    cudaError_t e;
-    if (k == SpmvKernel::Window)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_window_kernel, WARPS * 32, 0);
-    else if (k == SpmvKernel::Ldg)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<false, TB_LDG, false>,
-                                                          WARPS * 32, 0);
-    else
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<true, TB_TMA, false>,
-                                                          WARPS * 32, Geo<TB_TMA>::DYN_SMEM);
-    if (e != cudaSuccess || blocks <= 0) return 32;
-    return blocks * WARPS;
+    return variant_resident_blocks(selected_variant()) * WARPS;
 }
 
-int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals,
+const char* cvr_spmv_kernel_name()
+{
+    return VARIANTS[selected_variant()].name;
+}
+
+int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, int64_t nnz, const double* vals,
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
                     int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
                     cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end,
                     const CvrBarrier* barrier, unsigned int* done_counter, bool y_is_clear)
 {
     int launched = 0;
-    const SpmvKernel k = selected_kernel();
+    const int v = selected_variant();
+    const int sms = device_sm_count();
     const int32_t n_clear = rows.n_boundary + rows.n_empty;
     bool after_clear_kernel = false;
     if (y_is_clear) {
         // the previous iteration's epilogue kernel already cleared the accumulated rows
-    } else if (rows.boundary && k != SpmvKernel::Window) {
+    } else if (rows.boundary) {
         const int cb = (n_clear + 255) / 256;
-        cvr_clear_rows_kernel<<<cb < 1184 ? (cb < 1 ? 1 : cb) : 1184, 256, 0, stream>>>(
+        const int cap = sms * 8;
+        cvr_clear_rows_kernel<<<cb < cap ? (cb < 1 ? 1 : cb) : cap, 256, 0, stream>>>(
             y, rows.boundary, rows.n_boundary, rows.empty, rows.n_empty, publish && (publish->mode & 4));
         launched++;
         after_clear_kernel = true;
@@ -765,75 +1003,38 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, const double* vals
     }
     const int threads = WARPS * 32;
     const int blocks = (int)(((int64_t)n_chunks * 32 + threads - 1) / threads);
-    // the tile kernels are persistent: one block per resident slot, warps stride over the chunks
-    int resident_blocks = 0;
-    {
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        resident_blocks = sms * (cvr_spmv_resident_warps_per_sm() / WARPS);
-    }
-    const int pblocks = blocks < resident_blocks ? blocks : resident_blocks;
+    // the sweeps are persistent: one block per resident slot, warps stride over the chunks
+    const int resident = sms * variant_resident_blocks(v);
+    const int pblocks = blocks < resident ? blocks : resident;
     CvrPublish none{};
     const bool pub = publish && publish->n_dst > 0;
-    if (pub && k == SpmvKernel::Window) return -1;
+    // the kernel in front of us on the stream is the clearing kernel or (iterated SpMV, from the second
+    // iteration on) the previous iteration's epilogue: launch as its programmatic dependent
+    const bool programmatic = pdl_enabled() && (after_clear_kernel || (pub && y_is_clear)) && !ev_begin;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
-    if (k == SpmvKernel::Window)
-        cvr_spmv_window_kernel<<<blocks, threads, 0, stream>>>(chunks, n_chunks, vals, cols, record, x, y);
-    else if (k == SpmvKernel::Ldg) {
+    cudaError_t e = cudaSuccess;
+    if (!VARIANTS[v].pipe) {
         if (pub)
-            cvr_spmv_tile_kernel<false, TB_LDG, true><<<pblocks, threads, 0, stream>>>(
-                chunks, n_chunks, vals, cols, record, x, y, *publish);
+            e = launch_ex(cvr_spmv_tile_kernel<TB_TILE, true>, pblocks, threads, Geo<TB_TILE>::DYN_SMEM, stream,
+                          programmatic, chunks, n_chunks, vals, cols, record, x, y, *publish);
         else
-            cvr_spmv_tile_kernel<false, TB_LDG, false><<<pblocks, threads, 0, stream>>>(
-                chunks, n_chunks, vals, cols, record, x, y, none);
+            e = launch_ex(cvr_spmv_tile_kernel<TB_TILE, false>, pblocks, threads, Geo<TB_TILE>::DYN_SMEM, stream,
+                          programmatic, chunks, n_chunks, vals, cols, record, x, y, none);
     } else {
-        if (pub) {
-            // iterated SpMV: from the second iteration on the kernel in front of us is the previous
-            // iteration's epilogue (publish + barrier): launch as its programmatic dependent
-            static const bool use_pdl_pub = [] {
-                const char* e = getenv("CVR_NO_PDL");
-                return !(e && *e == '1');
-            }();
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(pblocks);
-            cfg.blockDim = dim3(threads);
-            cfg.dynamicSmemBytes = Geo<TB_TMA>::DYN_SMEM;
-            cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = (use_pdl_pub && (y_is_clear || after_clear_kernel) && !ev_begin) ? 1 : 0;
-            cudaLaunchKernelEx(&cfg, cvr_spmv_tile_kernel<true, TB_TMA, true>, chunks, n_chunks, vals, cols, record,
-                               x, y, *publish);
-        } else {
-            // ordinary SpMV: launch the sweep as a programmatic dependent of the clearing kernel
-            static const bool use_pdl = [] {
-                const char* e = getenv("CVR_NO_PDL");
-                return !(e && *e == '1');
-            }();
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(pblocks);
-            cfg.blockDim = dim3(threads);
-            cfg.dynamicSmemBytes = Geo<TB_TMA>::DYN_SMEM;
-            cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = (use_pdl && after_clear_kernel && !ev_begin) ? 1 : 0;
-            cudaLaunchKernelEx(&cfg, cvr_spmv_tile_kernel<true, TB_TMA, false>, chunks, n_chunks, vals, cols,
-                               record, x, y, none);
-        }
+        CVR_FOR_PIPE_VARIANT(v, e = P::launch(pub, pblocks, stream, programmatic, chunks, n_chunks, nnz, vals, cols,
+                                              record, x, y, pub ? *publish : none))
     }
+    if (e != cudaSuccess) return -1;
     launched++;
     if (ev_end) cudaEventRecord(ev_end, stream);
     if (pub) {
         if (!barrier || !done_counter) return -1;
         const int cb = (n_clear + 255) / 256;
-        cvr_publish_epilogue_kernel<<<cb < 592 ? (cb < 1 ? 1 : cb) : 592, 256, 0, stream>>>(
-            y, rows.boundary, rows.n_boundary, rows.empty, rows.n_empty, *publish, *barrier, done_counter);
+        const int cap = sms * 4;
+        e = launch_ex(cvr_publish_epilogue_kernel, cb < cap ? (cb < 1 ? 1 : cb) : cap, 256, 0, stream,
+                      pdl_enabled() && !ev_end, y, (const int32_t*)rows.boundary, rows.n_boundary,
+                      (const int32_t*)rows.empty, rows.n_empty, *publish, *barrier, done_counter);
+        if (e != cudaSuccess) return -1;
         launched++;
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
@@ -872,7 +1073,7 @@ int cvr_launch_chunk_needs(const CvrChunk* chunks, int32_t n_chunks, const uint8
 
 int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used, cudaStream_t stream)
 {
-    cvr_column_footprint_kernel<<<148 * 16, 256, 0, stream>>>(cols, nnz, used);
+    cvr_column_footprint_kernel<<<device_sm_count() * 16, 256, 0, stream>>>(cols, nnz, used);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -132,6 +132,7 @@ class PeerPublisher:
         for parity in (0, 1):
             p = _lib.CvrPublish()
             p.n_dst = world
+            p.self = rank  # dst[rank] is this GPU's own buffer (y aliases its slice of it, mode bit 2)
             p.mode = int(os.environ.get("CVR_PUBLISH_MODE", "0"))
             p.row_offset = self.cuts[rank] - 1
             p.needs = self.needs.data_ptr() if self.needs is not None else None

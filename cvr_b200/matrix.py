@@ -191,6 +191,31 @@ class CvrMatrix:
         return out
 
 
+def _csr_desc(csr):
+    desc = _lib.CvrCsr()
+    desc.n_rows, desc.n_cols, desc.nnz = csr.n_rows, csr.n_cols, csr.nnz
+    desc.val, desc.col = _ptr(csr.val), _ptr(csr.col)
+    rd = csr.row_delim
+    wide = (rd.dtype == np.int64) if isinstance(rd, np.ndarray) else ("int64" in str(rd.dtype))
+    desc.row_delim32 = 0 if wide else _ptr(rd)
+    desc.row_delim64 = _ptr(rd) if wide else 0
+    return desc
+
+
+def verify_csr(csr: DeviceCsr, x_dev, y_dev, rel_tol: float = 1e-12, check_row0: bool = True) -> dict:
+    """The self-check on the device (cvr_verify_csr): y against the CSR product, row by row,
+    |dy| <= rel_tol * sum|a x|.  Returns {"rows_failing", "max_rel", "first_bad_row"}."""
+    lib = _lib.load()
+    import torch
+    device = csr.device.index if csr.device.index is not None else 0
+    torch.cuda.synchronize(device)
+    bad, first, rel = C.c_int64(), C.c_int64(), C.c_double()
+    desc = _csr_desc(csr)
+    _lib.check(lib.cvr_verify_csr(C.byref(desc), int(device), _ptr(x_dev), _ptr(y_dev), float(rel_tol),
+                                  int(check_row0), C.byref(bad), C.byref(rel), C.byref(first)))
+    return {"rows_failing": bad.value, "max_rel": rel.value, "first_bad_row": first.value}
+
+
 def pre_processing(csr, n_threads: int = 0, device: int = 0) -> CvrMatrix:
     """CSR -> CVR on the GPU (spmv.cpp:565).  n_threads = number of chunks; 0 = auto."""
     return CvrMatrix(csr, n_threads, device)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CVR_B200_ABI_VERSION 1
+#define CVR_B200_ABI_VERSION 2
 #define CVR_LANES 8 /* SIMD_LEN for fp64, spmv.cpp:43 -- fixed by the bit-exact contract */
 
 typedef enum cvr_status {
@@ -153,6 +153,7 @@ int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* c
 #define CVR_MAX_PEERS 8
 typedef struct cvr_publish {
     int32_t n_dst;       /* 1..CVR_MAX_PEERS destinations, own buffer included */
+    int32_t self;        /* index of this GPU's own buffer in dst[] (required with mode bit 2) */
     int32_t mode;        /* bit 0: per-row stores instead of the coalesced per-chunk push (A/B);
                             bit 1: skip the 0.0 for never-written rows (set from the 3rd iteration on);
                             bit 2: y_dev IS this GPU's own slice of the next x (x_next + row_offset), so
@@ -174,6 +175,11 @@ typedef struct cvr_publish {
 int cvr_spmv_publish(cvr_handle_t* h, const double* x_dev, double* y_dev, const cvr_publish_t* pub,
                      void* const* flag_arrays, int32_t rank, int32_t n_ranks, uint32_t epoch,
                      int32_t y_is_clear, void* cuda_stream);
+/* The flag barrier spins for at most CVR_BARRIER_TIMEOUT_MS (default 3000 ms) so that a lost peer
+ * cannot hang the GPU; a timeout is recorded on the device.  Call this after synchronising (end of an
+ * iteration loop): CVR_ERR_STATE if a barrier of this handle timed out since the last call -- the
+ * x vectors are then stale and the results must be discarded. */
+int cvr_check_async_error(cvr_handle_t* h);
 /* used_dev[c] = 1 for every column id c (0..n_cols) that occurs in the shard: the x entries this
  * GPU actually reads.  Exchanged once, it lets every GPU publish a row only to the peers that
  * read it (a banded matrix then sends halos, not the whole vector). */
@@ -188,6 +194,15 @@ int cvr_peer_free(int device, void* dev_ptr);
  * epoch must increase by one per call.  Enqueued on cuda_stream. */
 int cvr_peer_barrier(int device, void* const* flag_arrays, int32_t rank, int32_t n_ranks, uint32_t epoch,
                      void* cuda_stream);
+
+/* Replaces the reference's self-check (spmv.cpp:1843-1850 scalar CSR SpMV, :1916-1938 comparison) on
+ * the device: y_dev against the CSR product of `csr_dev` (DEVICE pointers) and x_dev, row by row,
+ * |y_r - sum_j a_rj x_j| <= rel_tol * sum_j |a_rj x_j| for rows 1..n_rows (row 0, the phantom, must be
+ * 0.0 when check_row0 != 0).  Unlike the reference it checks the last row and uses a relative bound.
+ * Outputs: number of rows outside the bound, the largest relative error seen, the first bad row (-1). */
+int cvr_verify_csr(const cvr_csr_t* csr_dev, int device, const double* x_dev, const double* y_dev,
+                   double rel_tol, int check_row0, int64_t* rows_failing, double* max_rel,
+                   int64_t* first_bad_row);
 
 /* Bit-exact gate: copy the CVR structure arrays back in the reference layout. */
 int cvr_export(cvr_handle_t* h, cvr_arrays_t* host_out);
