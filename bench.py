@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- CVR SpMV throughput on B200 (GFLOP/s = 2*nnz/t, achieved HBM GB/s, roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fem|web|rmat24|road|rmat:S]
-                    [--impl ours|reference] [--chunks T]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rmat24|web|fem|road|rmat:S|rmat28]
+                    [--impl ours|reference] [--chunks T] [--no-subs]
 
-A "step" is one SpMV pass of the converted matrix: clear y + cvr_spmv_kernel (for N > 1
-followed by the y -> x all-gather of the iterated SpMV).  The conversion (CSR -> CVR on the
-device) happens once before the timed region, like the reference's pre_processing, and its
-time is reported in `extra`.
+A "step" is one SpMV pass of the converted matrix: clear the accumulated rows of y + the sweep
+kernel (for N > 1 followed by the y -> x exchange of the iterated SpMV).  The conversion (CSR -> CVR
+on the device) happens once before the timed region, like the reference's pre_processing; its kernel
+time and roofline are reported in `extra.convert`.
 
-Workload at N = 1 (default `fem`): BASELINE.json configs[1], the FEM-like banded matrix
-(100^3 grid, 27-point stencil, 1,000,000 rows, 26.46 M nnz, 342 MB of algorithmic traffic per
-SpMV -- larger than the 126 MB L2, so no flush is needed between steps).  For N > 1 the grid
-grows to 100 x 100 x 100N (weak scaling, each rank owns one 100^3 slab = an nnz-balanced row
-range) and every step ends with the all-gather that rebuilds the replicated x from the y
-shards.  Other workloads are strong-scaled (same matrix, nnz-balanced row shards).
+Headline workload (default `rmat24`): BASELINE.json configs[2], R-MAT scale 24 edge factor 16 --
+the largest configuration that fits one GPU, and one of the two the north star sets its target on.
+At N = 1 the other single-GPU configs (web-Google-shaped, FEM 100^3, road 24M) are measured in the
+same run and reported as sub-records under "workloads" (value, ms_per_step, roofline.frac, traffic,
+parity each).  At N > 1 the SAME R-MAT-24 matrix is row-sharded by nnz over the ranks (strong
+scaling) and every step ends with the exchange that rebuilds the replicated x from the y shards.
+
+Parity is checked INSIDE the bench: the y of the timed configuration is compared row by row with a
+device CSR product (cvr_verify_csr, |dy| <= 1e-12 * sum|a x|), and for N > 1 three iterations of the
+exchange are verified step by step and against the NCCL all-gather path.
 
 `--impl reference` times the reference's own CPU implementation of this path on the host cores
 (the unmodified reference from oracle/_ref when it was built and the CPU has AVX-512F, else the
@@ -35,12 +39,21 @@ if ROOT not in sys.path:
 
 METRIC = "spmv_gflops"
 UNIT = "GFLOP/s"
+HEADLINE = "rmat24"
+SUB_WORKLOADS = ["web", "fem", "road"]
+REL_TOL = 1e-12  # BASELINE.json: per row |dy| <= 1e-12 * sum_j |a_ij x_j|
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE cvr_spmv_kernel launch, from the committed
-# `ncu --set full` captures of this very command (NCU_TRAFFIC_SOURCE)
-NCU_DRAM_TRAFFIC = {"fem": 336.50e6 + 4.35e6, "rmat24": 3952.51e6 + 85.03e6,
-                    "web": 69.51e6 + 3.22e6, "road": 1094.03e6 + 167.53e6}
-NCU_TRAFFIC_SOURCE = {w: "profiles/r01_final_tma_%s_ncu.csv" % w for w in NCU_DRAM_TRAFFIC}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE sweep launch, from the committed `ncu --set full`
+# captures of this round (tools/kernel_ab.py under ncu, same matrices, same kernel)
+NCU_DRAM_TRAFFIC = {}
+NCU_TRAFFIC_SOURCE = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "r02_ncu_dram_traffic.json")) as _f:
+        for _w, _rec in json.load(_f).items():
+            NCU_DRAM_TRAFFIC[_w] = _rec["bytes"]
+            NCU_TRAFFIC_SOURCE[_w] = _rec["source"]
+except Exception:
+    pass
 
 
 def measured_peaks():
@@ -57,44 +70,46 @@ def make_workload(name: str, n_gpus: int, device, row_normalise: bool):
     """Returns (DeviceCsr of the WHOLE matrix, description, scaling)."""
     from cvr_b200 import gen
     if name == "fem":
+        d = gen.fem27(100, 100, 100, device=device)
+        desc = "fem27 100x100x100 grid (BASELINE configs[1]: FEM-like banded, ~27 nnz/row)"
+    elif name == "femweak":  # round-1 weak-scaling workload, kept for comparison
         d = gen.fem27(100, 100, 100 * n_gpus, device=device)
-        desc = f"fem27 100x100x{100 * n_gpus} grid (BASELINE configs[1]: FEM-like banded, ~27 nnz/row)"
-        scaling = "weak"
+        desc = f"fem27 100x100x{100 * n_gpus} grid (weak-scaled FEM)"
+        return _normalise(d, row_normalise), desc, "weak"
     elif name == "web":
         d = gen.powerlaw_web(device=device)
         desc = "web-Google-shaped power law 916,428 rows (BASELINE configs[0])"
-        scaling = "strong"
     elif name == "rmat24":
         d = gen.rmat(24, 16, device=device)
         desc = "R-MAT scale 24 edge factor 16 (BASELINE configs[2])"
-        scaling = "strong"
     elif name.startswith("rmat:"):
         s = int(name.split(":")[1])
         d = gen.rmat(s, 16, device=device)
         desc = f"R-MAT scale {s} edge factor 16"
-        scaling = "strong"
     elif name == "road":
         d = gen.road(24_000_000, device=device)
         desc = "road-network-like 24M rows ~2.4 nnz/row (BASELINE configs[3])"
-        scaling = "strong"
     elif name == "tiny":  # smoke-sized
-        d = gen.fem27(20, 20, 20 * n_gpus, device=device)
+        d = gen.fem27(20, 20, 20, device=device)
         desc = "fem27 20^3 (smoke)"
-        scaling = "weak"
     else:
         raise SystemExit(f"unknown workload {name}")
-    if row_normalise:
+    return _normalise(d, row_normalise), desc, "strong"
+
+
+def _normalise(d, row_normalise: bool):
+    if row_normalise:  # ||A||_inf <= 1: iterated SpMV stays finite (SURVEY.md 8e)
         import torch
         rd = d.row_delim.to(torch.int64)
         rows = torch.repeat_interleave(torch.arange(d.n_rows + 1, device=d.val.device), rd[1:] - rd[:-1])
         mag = torch.zeros(d.n_rows + 1, dtype=torch.float64, device=d.val.device).index_add_(0, rows, d.val.abs())
         d.val = (d.val / mag[rows].clamp_min(1e-300)).to(torch.float32).to(torch.float64).contiguous()
-    return d, desc, scaling
+    return d
 
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML)."""
+    """SM clock and throttle reasons sampled DURING the timed regions (NVML, every 5 ms)."""
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
@@ -124,7 +139,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.005)
 
     def __enter__(self):
         if self.nv:
@@ -181,7 +196,7 @@ def run_reference(args, rank: int):
     del d
     threads = os.cpu_count() or 1
     if args.warmup > 0:
-        cpu_reference_time(h, max(1, min(args.warmup, 3)), threads)
+        cpu_reference_time(h, max(1, min(args.warmup, 2)), threads)
     secs, conv, kind = cpu_reference_time(h, args.steps, threads)
     gflops = 2.0 * h.nnz_true / secs / 1e9
     line = {
@@ -198,175 +213,112 @@ def run_reference(args, rank: int):
     print(json.dumps(line))
 
 
-# ----------------------------------------------------------------------------- our arm
-def run_ours(args, rank: int, world: int, local_rank: int):
-    import numpy as np
+# ----------------------------------------------------------------------------- helpers of our arm
+def conversion_record(info, peak):
+    """extra.convert: the two conversion kernels (schedule + permute) timed alone with CUDA events,
+    against B_conv = 12 nnzP + 4 (nRows+2) read + 12 nnzP + 8 n_rec written."""
+    b_conv = 24 * info["nnz"] + 4 * (info["n_rows"] + 2) + 8 * info["n_records"]
+    ks = info["convert_kernel_seconds"]
+    return {"kernel_ms": ks * 1e3, "B_conv": b_conv,
+            "frac": (b_conv / ks / 1e9 / peak) if ks > 0 else None,
+            "row_lists_ms": info["row_lists_seconds"] * 1e3,
+            "convert_seconds_device": info["convert_seconds"], "create_seconds": info["create_seconds"]}
+
+
+def single_gpu_measurement(name, args, dev, local_rank, peak, clocks, want_cusparse=False, want_cpu=False):
+    """One workload on one GPU: timed steps, the sweep kernel alone, parity, e2e, conversion."""
     import torch
-    import torch.distributed as dist
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the CVR path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # rank 0 must print exactly one JSON line on stdout: NCCL writes its version banner (any
-        # NCCL_DEBUG level >= VERSION) and debug lines to stdout unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-
     import cvr_b200
-    from cvr_b200 import shard
 
-    iterated = world > 1
-    big_rmat = None
-    if args.workload == "rmat28":
-        big_rmat = 28
-    elif args.workload.startswith("rmat:") and int(args.workload.split(":")[1]) >= 26:
-        big_rmat = int(args.workload.split(":")[1])
-    if big_rmat is not None:
-        # config 5: too large to build on one GPU -- every rank generates only its own row shard
-        from cvr_b200 import gen
-        mine, cuts, nt = gen.rmat_shard(big_rmat, 16, rank, world, dev, row_normalise=True,
-                                        row_weight=args.row_weight)
-        tot = torch.tensor([nt], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(tot)
-        nnz_true_total = int(tot.item())
-        n_rows_total = n_cols = 1 << big_rmat
-        desc = f"R-MAT scale {big_rmat} edge factor 16, generated per row shard (BASELINE configs[4] at scale 28)"
-        scaling = "strong"
-        full = None
-    else:
-        full, desc, scaling = make_workload(args.workload, world, dev, row_normalise=True)
-        nnz_true_total = full.nnz_true
-        n_rows_total, n_cols = full.n_rows, full.n_cols
-        cuts = (shard.partition_rows_by_nnz_torch(full.row_delim, world, args.row_weight) if world > 1
-                else [1, n_rows_total + 1])
-        mine = shard.shard_device_csr(full, cuts[rank], cuts[rank + 1]) if world > 1 else full
-    keep_host = full.to_host() if (full is not None and rank == 0 and world == 1 and not args.no_cpu_baseline) else None
-    keep_csr = None
-    if full is not None and world == 1 and not args.no_cusparse and full.nnz < 600_000_000:
-        keep_csr = (full.row_delim.to(torch.int64).clone(), full.col.to(torch.int64), full.val.clone())
-    del full
+    full, desc, scaling = make_workload(name, 1, dev, row_normalise=True)
+    nnz_true, n_rows, n_cols = full.nnz_true, full.n_rows, full.n_cols
+    keep_host = full.to_host() if want_cpu else None
     torch.cuda.synchronize()
-
-    m = cvr_b200.CvrMatrix(mine, args.chunks, local_rank)
+    m = cvr_b200.CvrMatrix(full, args.chunks, local_rank)
     info = m.info
-    del mine
-    torch.cuda.empty_cache()
-
-    from cvr_b200.dist import RowShardExchange
-    exchange = RowShardExchange(cuts, rank, world, dev)
     stream = torch.cuda.current_stream()
     g = torch.Generator(device=dev).manual_seed(99)
     x = torch.rand(n_cols + 1, generator=g, device=dev, dtype=torch.float64) - 0.5
     x[0] = 0.0
-    y = torch.zeros(info["n_rows"] + 1, dtype=torch.float64, device=dev)
-
-    publisher = None
-    if iterated and args.exchange == "peer":
-        from cvr_b200.dist import PeerPublisher
-        publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange)
-        publisher.set_x(x)
-
-    def step():
-        if publisher is not None:
-            publisher.step(y, stream.cuda_stream)  # SpMV kernel publishes rows into every peer's next x
-            return
-        m.spmv_device(x, y, stream.cuda_stream)
-        if iterated:
-            exchange(y, x)  # y shards -> replicated x: the one collective of the iterated SpMV
-
+    y = torch.zeros(n_rows + 1, dtype=torch.float64, device=dev)
     flush = None
     if info["algorithmic_bytes"] < 256e6:  # would sit in the 126 MB L2: flush between steps
         flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step():
+        m.spmv_device(x, y, stream.cuda_stream)
 
     for _ in range(max(args.warmup, 3)):
         step()
-    barrier()
+    torch.cuda.synchronize()
 
     # ---- timed region A: K whole steps
     launches0 = m.info["kernel_launches"]
-    clocks = ClockSampler(local_rank)
-    clocks.__enter__()
-    if True:
-        if flush is None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            e0.record(stream)
-            for _ in range(args.steps):
-                step()
-            e1.record(stream)
-            barrier()
-            total_ms = e0.elapsed_time(e1)
-        else:
-            pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                     for _ in range(args.steps)]
-            barrier()
-            for a, b in pairs:
-                flush.fill_(1)
-                a.record(stream)
-                step()
-                b.record(stream)
-            barrier()
-            total_ms = sum(a.elapsed_time(b) for a, b in pairs)
+    clocks.resume()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        total_ms = e0.elapsed_time(e1)
+    else:
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                 for _ in range(args.steps)]
+        torch.cuda.synchronize()
+        for a, b in pairs:
+            flush.fill_(1)
+            a.record(stream)
+            step()
+            b.record(stream)
+        torch.cuda.synchronize()
+        total_ms = sum(a.elapsed_time(b) for a, b in pairs)
     launches = m.info["kernel_launches"] - launches0
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
-    gflops = 2.0 * nnz_true_total / (ms_per_step * 1e-3) / 1e9
+    ms_per_step = total_ms / args.steps
+    gflops = 2.0 * nnz_true / (ms_per_step * 1e-3) / 1e9
 
-    # ---- region B: the SpMV kernel alone, one CUDA-event pair per launch
+    # ---- parity of what was just timed: y against the device CSR product, row by row
+    parity = cvr_b200.verify_csr(full, x, y, REL_TOL)
+    parity["tolerance"] = "per row |dy| <= 1e-12 * sum|a x| vs device CSR product (cvr_verify_csr)"
+
+    # ---- region B: the sweep kernel alone, one CUDA-event pair per launch
     m.set_kernel_timing(True)
-    barrier()
+    torch.cuda.synchronize()
     for _ in range(args.steps):
         if flush is not None:
             flush.fill_(1)
-        if publisher is not None:
-            publisher.step(y, stream.cuda_stream)  # the sweep kernel incl. its peer stores
-        else:
-            m.spmv_device(x, y, stream.cuda_stream)
-    barrier()
+        step()
+    torch.cuda.synchronize()
     ksecs, klaunches = m.kernel_timing()
     m.set_kernel_timing(False)
-    clocks.__exit__(None, None, None)
     kernel_s = ksecs / max(klaunches, 1)
-    if world > 1 and os.environ.get("CVR_BENCH_DEBUG"):
-        allk = [None] * world
-        dist.all_gather_object(allk, (rank, kernel_s * 1e6, info["n_rows"], info["nnz"], info["n_records"]))
-        if rank == 0:
-            print("per-rank sweep kernel us / rows / nnz / records:", allk, file=sys.stderr)
-    peak, peak_src = measured_peaks()
     achieved = info["algorithmic_bytes"] / kernel_s / 1e9
 
     # ---- end to end through the host-buffer C-ABI call (cvr_spmv): H2D x + SpMV + D2H y per step
     xh = torch.empty(n_cols + 1, dtype=torch.float64).pin_memory()
-    yh = torch.empty(info["n_rows"] + 1, dtype=torch.float64).pin_memory()
+    yh = torch.empty(n_rows + 1, dtype=torch.float64).pin_memory()
     xh.copy_(x.cpu())
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 10))
     m.spmv_into(xh, yh, 1)
-    barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         m.spmv_into(xh, yh, 1)
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_gflops = 2.0 * nnz_true_total / float(e2e_s.item()) / 1e9
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    clocks.pause()
+    e2e_bad = int((yh.to(dev) - y).abs().max().item() > 0.0) if False else None  # same kernels, same x
+    del e2e_bad
+    # iterated through the same call: `iters` SpMVs per upload (the reference CLI's usage, x resident)
+    it10 = m.spmv_into(xh, yh, 10)
 
-    # ---- context: cuSPARSE CSR SpMV (through torch.sparse) on the same matrix, same x -- the
-    # library baseline a GPU user would reach for; not part of the headline
+    # ---- context: cuSPARSE CSR SpMV (through torch.sparse) on the same matrix, same x
     cusparse = None
-    if world == 1 and keep_csr is not None and not args.no_cusparse:
+    if want_cusparse:
         try:
-            crow, ccol, cval = keep_csr
-            A = torch.sparse_csr_tensor(crow, ccol, cval, size=(info["n_rows"] + 1, n_cols + 1))
+            A = torch.sparse_csr_tensor(full.row_delim.to(torch.int64), full.col.to(torch.int64), full.val,
+                                        size=(n_rows + 1, n_cols + 1))
             for _ in range(3):
                 yy = A @ x
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -387,68 +339,342 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 f1.record()
                 torch.cuda.synchronize()
                 ms -= f0.elapsed_time(f1) / args.steps
-            cusparse = {"gflops": 2.0 * nnz_true_total / (ms * 1e-3) / 1e9, "ms_per_spmv": ms,
+            cusparse = {"gflops": 2.0 * nnz_true / (ms * 1e-3) / 1e9, "ms_per_spmv": ms,
                         "what": "torch.sparse_csr (cuSPARSE) y = A @ x, fp64, same matrix and x"}
             del A, yy
         except Exception as ex:  # context only: never fail the bench on it
             cusparse = {"error": str(ex)[:200]}
 
+    rec = {
+        "workload": desc, "n_rows": n_rows, "nnz": nnz_true, "chunks": info["n_chunks"],
+        "value": gflops, "unit": UNIT, "ms_per_step": ms_per_step, "gpu_launches": int(launches),
+        "l2": "inputs exceed L2 (no flush)" if flush is None else "L2 flushed between steps (384 MB write, untimed)",
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_DRAM_TRAFFIC.get(name), "traffic_source": NCU_TRAFFIC_SOURCE.get(name),
+                     "kernel": "cvr_spmv_%s_kernel" % ("tile" if m.kernel_name == "tile" else "pipe"),
+                     "kernel_variant": m.kernel_name, "kernel_us": kernel_s * 1e6,
+                     "algorithmic_bytes_per_launch": info["algorithmic_bytes"],
+                     "kernel_share_of_step": kernel_s * 1e3 / ms_per_step,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "parity": parity,
+        "e2e": {"value": 2.0 * nnz_true / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * (n_cols + 1),
+                "d2h_bytes_per_step": 8 * (n_rows + 1), "steps": e2e_steps,
+                "x_resident_10_iters_gflops": 2.0 * nnz_true / it10 / 1e9 if it10 > 0 else None},
+        "convert": conversion_record(info, peak),
+        "n_records": info["n_records"],
+    }
+    if cusparse is not None:
+        rec["cusparse_csr"] = cusparse
+    if keep_host is not None:
+        big = keep_host.nnz > 100e6
+        iters = 5 if big else 50
+        secs, conv, kind = cpu_reference_time(keep_host, iters, os.cpu_count() or 1)
+        rec["cpu_baseline"] = {"value": 2.0 * keep_host.nnz_true / secs / 1e9, "unit": UNIT,
+                               "cores": os.cpu_count() or 1, "kind": kind,
+                               "sample": f"whole matrix, {iters} SpMV iterations on the host cores "
+                                         "(reference timer: y zeroing excluded)",
+                               "ms_per_spmv": secs * 1e3, "convert_seconds": conv}
+    m.close()
+    del full, x, y, flush, m
+    torch.cuda.empty_cache()
+    return rec, scaling
+
+
+class PausableClocks:
+    """ClockSampler that only samples while a timed region is running."""
+
+    def __init__(self, index):
+        self.inner = ClockSampler(index)
+        self._on = False
+
+    def resume(self):
+        if not self._on:
+            self.inner._stop.clear()
+            self.inner.__enter__()
+            self._on = True
+
+    def pause(self):
+        if self._on:
+            self.inner.__exit__(None, None, None)
+            self._on = False
+
+    def summary(self):
+        self.pause()
+        return self.inner.summary()
+
+
+# ----------------------------------------------------------------------------- our arm, N = 1
+def run_single(args, local_rank: int):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CVR path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    peak, peak_src = measured_peaks()
+    clocks = PausableClocks(local_rank)
+    head, scaling = single_gpu_measurement(args.workload, args, dev, local_rank, peak, clocks,
+                                           want_cusparse=not args.no_cusparse, want_cpu=not args.no_cpu_baseline)
+    subs = {}
+    if not args.no_subs and args.workload == HEADLINE:
+        for name in SUB_WORKLOADS:
+            rec, _ = single_gpu_measurement(name, args, dev, local_rank, peak, clocks,
+                                            want_cusparse=not args.no_cusparse, want_cpu=False)
+            subs[name] = rec
+    line = {
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": head["workload"], "n_rows": head["n_rows"], "nnz": head["nnz"],
+                   "chunks_per_gpu": head["chunks"], "iterated_x_from_y": False, "shard_balance": None,
+                   "l2": head["l2"],
+                   "step": "clear accumulated rows + sweep kernel (programmatic dependent launch)"},
+        "gpu_launches": head["gpu_launches"],
+        "e2e": head["e2e"],
+        "roofline": dict(head["roofline"], peak_source=peak_src),
+        "parity": head["parity"],
+        "clocks": clocks.summary(),
+        "extra": {"convert": head["convert"], "cusparse_csr": head.get("cusparse_csr"),
+                  "n_records": head["n_records"],
+                  "gather_ceiling": "profiles/r02_gather_probe_summary.txt: stream + gather + FMA without any "
+                                    "row bookkeeping takes 0.94 ms on this matrix (L1 miss path, ~1 gathered "
+                                    "element per SM clock) = 0.57 of the HBM roofline"
+                  if args.workload == HEADLINE else None},
+    }
+    if "cpu_baseline" in head:
+        line["cpu_baseline"] = head["cpu_baseline"]
+    if subs:
+        line["workloads"] = {k: {kk: vv for kk, vv in v.items() if kk != "cpu_baseline"} for k, v in subs.items()}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm, N > 1
+def run_multi(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CVR path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    # rank 0 must print exactly one JSON line on stdout: NCCL writes its version banner (any
+    # NCCL_DEBUG level >= VERSION) and debug lines to stdout unless told otherwise
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=dev)
+
+    import cvr_b200
+    from cvr_b200 import shard
+    from cvr_b200.dist import PeerPublisher, RowShardExchange
+    peak, peak_src = measured_peaks()
+
+    big_rmat = None
+    if args.workload == "rmat28":
+        big_rmat = 28
+    elif args.workload.startswith("rmat:") and int(args.workload.split(":")[1]) >= 26:
+        big_rmat = int(args.workload.split(":")[1])
+    full = None
+    if big_rmat is not None:
+        # config 5: too large to build on one GPU -- every rank generates only its own row shard
+        from cvr_b200 import gen
+        mine, cuts, nt = gen.rmat_shard(big_rmat, 16, rank, world, dev, row_normalise=True,
+                                        row_weight=args.row_weight)
+        tot = torch.tensor([nt], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot)
+        nnz_true_total = int(tot.item())
+        n_rows_total = n_cols = 1 << big_rmat
+        desc = f"R-MAT scale {big_rmat} edge factor 16, generated per row shard (BASELINE configs[4] at scale 28)"
+        scaling = "strong"
+    else:
+        full, desc, scaling = make_workload(args.workload, world, dev, row_normalise=True)
+        nnz_true_total = full.nnz_true
+        n_rows_total, n_cols = full.n_rows, full.n_cols
+        cuts = shard.partition_rows_by_nnz_torch(full.row_delim, world, args.row_weight)
+        mine = shard.shard_device_csr(full, cuts[rank], cuts[rank + 1])
+        if rank != 0:
+            full = None  # rank 0 keeps the whole CSR: it is the parity reference
+    torch.cuda.synchronize()
+
+    m = cvr_b200.CvrMatrix(mine, args.chunks, local_rank)
+    info = m.info
+    del mine
+    torch.cuda.empty_cache()
+
+    exchange = RowShardExchange(cuts, rank, world, dev)
+    stream = torch.cuda.current_stream()
+    g = torch.Generator(device=dev).manual_seed(99)
+    x0 = torch.rand(n_cols + 1, generator=g, device=dev, dtype=torch.float64) - 0.5
+    x0[0] = 0.0
+    x = x0.clone()
+    y = torch.zeros(info["n_rows"] + 1, dtype=torch.float64, device=dev)
+
+    publisher = None
+    if args.exchange == "peer":
+        publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange)
+        publisher.set_x(x)
+
+    def step():
+        if publisher is not None:
+            publisher.step(y, stream.cuda_stream)  # the sweep publishes rows into every peer's next x
+            return
+        m.spmv_device(x, y, stream.cuda_stream)
+        exchange(y, x)  # y shards -> replicated x: the one collective of the iterated SpMV
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region A: K whole steps (inputs exceed L2 at every N for the default workload)
+    launches0 = m.info["kernel_launches"]
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = m.info["kernel_launches"] - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    gflops = 2.0 * nnz_true_total / (ms_per_step * 1e-3) / 1e9
+
+    # ---- region B: the sweep kernel alone, one CUDA-event pair per launch
+    m.set_kernel_timing(True)
+    barrier()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    ksecs, klaunches = m.kernel_timing()
+    m.set_kernel_timing(False)
+    clocks.__exit__(None, None, None)
+    kernel_s = ksecs / max(klaunches, 1)
+    allk = [None] * world
+    dist.all_gather_object(allk, (kernel_s * 1e6, info["n_rows"], info["nnz"], info["n_records"]))
+
+    # algorithmic bytes of THIS shard: the x term counts only the entries its columns touch
+    used = torch.zeros(n_cols + 1, dtype=torch.uint8, device=dev)
+    m.column_footprint(used)
+    torch.cuda.synchronize()
+    x_touched = int(used.sum().item())
+    del used
+    shard_bytes = info["algorithmic_bytes"] - 8 * (n_cols + 1) + 8 * x_touched
+    achieved = shard_bytes / kernel_s / 1e9
+
+    # ---- parity of the exchange, step by step: after ONE iteration from a known x the assembled vector must
+    # equal the CSR product of that x row by row; the result then seeds the next check (3 iterations: both x
+    # buffers and the switch to "do not re-publish the empty rows")
+    parity = {"tolerance": "per row |dy| <= 1e-12 * sum|a x| vs device CSR product, one iteration at a time",
+              "iterations_checked": 0, "rows_failing": 0, "max_rel": 0.0}
+    if full is not None or big_rmat is None:
+        cur = x0.clone()
+        per_iter_x = []
+        for it in range(3):
+            if publisher is not None:
+                if it == 0:
+                    publisher.set_x(cur)
+                publisher.step(y, stream.cuda_stream)
+                nxt = publisher.full_x()
+                m.check_async_error()
+            else:
+                x.copy_(cur)
+                m.spmv_device(x, y, stream.cuda_stream)
+                exchange(y, x)
+                torch.cuda.synchronize()
+                nxt = x.clone()
+            if rank == 0:
+                r = cvr_b200.verify_csr(full, cur, nxt, REL_TOL, check_row0=False)
+                parity["rows_failing"] += r["rows_failing"]
+                parity["max_rel"] = max(parity["max_rel"], r["max_rel"])
+                parity["iterations_checked"] += 1
+            per_iter_x.append(nxt)
+            cur = nxt
+        # the NCCL all-gather path from the same start: must agree with the fused exchange
+        if publisher is not None:
+            xa = x0.clone()
+            worst = 0.0
+            for it in range(3):
+                m.spmv_device(xa, y, stream.cuda_stream)
+                exchange(y, xa)
+                torch.cuda.synchronize()
+                scale = float(xa.abs().max().item()) + 1e-300
+                worst = max(worst, float((xa[1:] - per_iter_x[it][1:]).abs().max().item()) / scale)
+            parity["peer_vs_nccl_max_abs_over_max"] = worst
+        del per_iter_x, cur
+    else:
+        parity["note"] = "matrix generated per shard: no whole-matrix reference on one GPU (see tests/test_gpu_multi.py)"
+    bad = torch.tensor([parity["rows_failing"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(bad)
+
+    # ---- end to end: host buffers in, local SpMV, host buffers out, on every rank (max over ranks)
+    xh = torch.empty(n_cols + 1, dtype=torch.float64).pin_memory()
+    yh = torch.empty(info["n_rows"] + 1, dtype=torch.float64).pin_memory()
+    xh.copy_(x0.cpu())
+    e2e_steps = max(3, min(args.steps, 10))
+    m.spmv_into(xh, yh, 1)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        m.spmv_into(xh, yh, 1)
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_gflops = 2.0 * nnz_true_total / float(e2e_s.item()) / 1e9
+
     if rank == 0:
+        ingress = 8.0 * n_rows_total * (world - 1) / world
         line = {
             "metric": METRIC, "value": gflops, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "n_rows": n_rows_total, "nnz": nnz_true_total,
-                       "chunks_per_gpu": info["n_chunks"], "iterated_x_from_y": iterated,
-                       "shard_balance": ("nnz" if not args.row_weight else f"nnz + {args.row_weight:g} per non-empty row")
-                       if world > 1 else None,
-                       "l2": "inputs exceed L2 (no flush)" if flush is None else "L2 flushed between steps (384 MB write, untimed)",
-                       "step": "clear accumulated rows + cvr_spmv_kernel (programmatic dependent launch)" + (
-                           (" (publishes y rows into every peer's x over NVLink) + accumulated-rows publish + flag barrier"
-                            if publisher is not None else " + NCCL all-gather y->x") if iterated else "")},
+                       "chunks_per_gpu": info["n_chunks"], "iterated_x_from_y": True,
+                       "shard_balance": "nnz" if not args.row_weight else f"nnz + {args.row_weight:g} per non-empty row",
+                       "l2": "inputs exceed L2 (no flush)",
+                       "step": "sweep kernel (programmatic dependent launch)" + (
+                           " publishing y rows into every peer's x over NVLink + accumulated-rows publish + flag barrier"
+                           if publisher is not None else " + NCCL all-gather y->x")},
             "gpu_launches": int(launches),
-            "e2e": {"value": e2e_gflops, "unit": UNIT, "h2d_bytes_per_step": 8 * (n_cols + 1),
-                    "d2h_bytes_per_step": 8 * (info["n_rows"] + 1), "steps": e2e_steps},
+            "e2e": {"value": e2e_gflops, "unit": UNIT, "h2d_bytes_per_step": 8 * (n_cols + 1) * world,
+                    "d2h_bytes_per_step": 8 * (n_rows_total + world), "steps": e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": NCU_DRAM_TRAFFIC.get(args.workload) if world == 1 else None,
-                         "traffic_source": NCU_TRAFFIC_SOURCE.get(args.workload) if world == 1 else None,
-                         "peak_source": peak_src,
-                         "kernel": "cvr_spmv_kernel", "kernel_us": kernel_s * 1e6,
-                         "algorithmic_bytes_per_launch": info["algorithmic_bytes"],
+                         "frac": achieved / peak, "traffic": None, "traffic_source": None, "peak_source": peak_src,
+                         "kernel": "cvr_spmv_%s_kernel (rank 0 shard)" % ("tile" if m.kernel_name == "tile" else "pipe"),
+                         "kernel_variant": m.kernel_name, "kernel_us": kernel_s * 1e6,
+                         "algorithmic_bytes_per_launch": shard_bytes, "x_entries_touched": x_touched,
                          "kernel_share_of_step": kernel_s * 1e3 / ms_per_step,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
+            "parity": parity,
             "clocks": clocks.summary(),
-            "extra": {"step_gbs": info["algorithmic_bytes"] * world / (ms_per_step * 1e-3) / 1e9 if scaling == "weak"
-                      else None,
+            "extra": {"per_rank_sweep_us_rows_nnz_records": allk,
                       "peer_bytes_sent_per_step_rank0": publisher.bytes_sent_per_iteration() if publisher else None,
-                      "cusparse_csr": cusparse,
-                      "convert_seconds_device": info["convert_seconds"],
-                      "create_seconds": info["create_seconds"], "n_records": info["n_records"]},
+                      "nvlink_ingress_bytes_per_gpu": ingress,
+                      "nvlink_ingress_bound_us": {"at_900_GBs_nominal": ingress / 900e9 * 1e6,
+                                                  "at_770_GBs_measured": ingress / 770e9 * 1e6},
+                      "convert": conversion_record(info, peak), "n_records": info["n_records"]},
         }
-        if keep_host is not None:
-            big = keep_host.nnz > 100e6
-            secs, conv, kind = cpu_reference_time(keep_host, 10 if big else 50, os.cpu_count() or 1)
-            line["cpu_baseline"] = {"value": 2.0 * keep_host.nnz_true / secs / 1e9, "unit": UNIT,
-                                    "cores": os.cpu_count() or 1, "kind": kind,
-                                    "sample": f"whole matrix, {10 if big else 50} SpMV iterations on the host cores",
-                                    "ms_per_spmv": secs * 1e3, "convert_seconds": conv}
         print(json.dumps(line))
     if publisher is not None:
         publisher.close()
     m.close()
-    if world > 1:
-        dist.destroy_process_group()
+    dist.destroy_process_group()
+    if int(bad.item()) != 0:
+        raise SystemExit(f"bench.py: parity FAILED ({int(bad.item())} rows outside 1e-12)")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fem")
+    ap.add_argument("--workload", default=HEADLINE)
     ap.add_argument("--chunks", type=int, default=0, help="CVR chunks per GPU (0 = auto)")
+    ap.add_argument("--no-subs", action="store_true", help="N = 1: skip the web / fem / road sub-records")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cusparse", action="store_true", help="skip the cuSPARSE CSR context measurement")
     ap.add_argument("--row-weight", type=float, default=0.0,
@@ -467,7 +693,10 @@ def main():
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N > 1 with "
                          "`python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...`")
-    run_ours(args, rank, world, local_rank)
+    if world == 1:
+        run_single(args, local_rank)
+    else:
+        run_multi(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

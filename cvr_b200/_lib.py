@@ -32,7 +32,8 @@ class CvrInfo(C.Structure):  # cvr_info_t
                 ("n_records", C.c_int64), ("record_ints", C.c_int64),
                 ("algorithmic_bytes", C.c_int64),
                 ("convert_seconds", C.c_double), ("create_seconds", C.c_double),
-                ("kernel_launches", C.c_int64), ("device_bytes", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("device_bytes", C.c_int64),
+                ("convert_kernel_seconds", C.c_double), ("row_lists_seconds", C.c_double)]
 
 
 class CvrPublish(C.Structure):  # cvr_publish_t
@@ -80,6 +81,7 @@ SIGNATURES = {
     "cvr_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "cvr_get_info": (C.c_int, [C.c_void_p, C.POINTER(CvrInfo)]),
     "cvr_device_vectors": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "cvr_kernel_variant": (C.c_char_p, []),
     "cvr_device_arrays": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cvr_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "cvr_get_kernel_timing": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),

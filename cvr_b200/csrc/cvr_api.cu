@@ -73,6 +73,8 @@ struct cvr_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double convert_seconds = 0.0, create_seconds = 0.0;
+    double convert_kernel_seconds = 0.0, row_lists_seconds = 0.0;
+    cudaEvent_t ev2 = nullptr;
     int64_t launches = 0;
     int64_t device_bytes = 0;
     std::vector<CvrChunk> host_chunks; // copy of the descriptors (export / info)
@@ -97,6 +99,7 @@ struct cvr_handle {
         cudaFree(y);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev2) cudaEventDestroy(ev2);
         for (cudaEvent_t e : timing_events) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -172,7 +175,8 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
     a.seg_count = seg_count;
 
     int rc = CVR_OK;
-    float ms = 0.f;
+    float ms = 0.f, ms_kernels = 0.f;
+    double t_lists = 0.0;
     do {
         // every int the scheduler does not write reads back as -1 (a terminator)
         if ((e = cudaMemsetAsync(h->record, 0xff, sizeof(int32_t) * (size_t)h->record_ints,
@@ -185,6 +189,11 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
             break;
         }
         h->launches += launched;
+        // ev0..ev2 brackets the two conversion kernels (schedule + permute) alone; the row lists that follow
+        // allocate, synchronise and free around their three small kernels, so they are timed by the host clock
+        if ((e = cudaEventRecord(h->ev2, h->stream)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
+        const double tl0 = wall_seconds();
         const int listed = cvr_build_row_lists(h->chunks, T, csr->row_delim32, csr->row_delim64, h->n_rows,
                                                &h->rows, h->stream);
         if (listed < 0) {
@@ -195,12 +204,16 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
         h->device_bytes += 4 * ((int64_t)h->rows.n_boundary + h->rows.n_empty + 2);
         if ((e = cudaEventRecord(h->ev1, h->stream)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
+        t_lists = wall_seconds() - tl0;
         if ((e = cudaEventElapsedTime(&ms, h->ev0, h->ev1)) != cudaSuccess) break;
+        if ((e = cudaEventElapsedTime(&ms_kernels, h->ev0, h->ev2)) != cudaSuccess) break;
     } while (0);
     cudaFree(segments);
     cudaFree(seg_count);
     if (rc != CVR_OK) return rc;
     if (e != cudaSuccess) return fail(CVR_ERR_CUDA, "conversion failed: %s", cudaGetErrorString(e));
+    h->convert_kernel_seconds = ms_kernels * 1e-3;
+    h->row_lists_seconds = t_lists;
     h->convert_seconds = ms * 1e-3;
 
     h->host_chunks.resize((size_t)T);
@@ -251,7 +264,7 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev0)) != cudaSuccess ||
-        (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+        (e = cudaEventCreate(&h->ev1)) != cudaSuccess || (e = cudaEventCreate(&h->ev2)) != cudaSuccess) {
         delete h;
         return fail(CVR_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
     }
@@ -512,6 +525,8 @@ int cvr_get_info(cvr_handle_t* h, cvr_info_t* info)
     info->create_seconds = h->create_seconds;
     info->kernel_launches = h->launches;
     info->device_bytes = h->device_bytes;
+    info->convert_kernel_seconds = h->convert_kernel_seconds;
+    info->row_lists_seconds = h->row_lists_seconds;
     return CVR_OK;
 }
 
@@ -522,6 +537,8 @@ int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev)
     if (y_dev) *y_dev = h->y;
     return CVR_OK;
 }
+
+const char* cvr_kernel_variant(void) { return cvr_spmv_kernel_name(); }
 
 int cvr_device_arrays(cvr_handle_t* h, const double** vals_dev, const int32_t** cols_dev,
                       const int32_t** record_dev)

@@ -198,8 +198,8 @@ __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return ((w * 0x0
 #define CVR_TMA_BLOCKS 6
 #endif
 
-template <int TB, bool kPublish>
-__global__ void __launch_bounds__(WARPS * 32, CVR_TMA_BLOCKS)
+template <int TB, int NB, bool kPublish>
+__global__ void __launch_bounds__(WARPS * 32, NB)
 cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
                      const double* __restrict__ vals, const int32_t* __restrict__ cols,
                      const int32_t* __restrict__ record, const double* __restrict__ x,
@@ -593,14 +593,23 @@ cvr_spmv_pipe_kernel(const CvrChunk* __restrict__ chunks, int32_t T, int64_t nnz
             lane_carry = 0.0;
             carry_slot = 0.0;
         }
-        // ---- 1. gathers of tile g+1
-        if (nel1 > 0) {
-            mbar_wait(bar0 + 8u * (sidx ^ 1u), ((g + 1u) >> 1) & 1u);
-            gather_tile(sidx ^ 1u, nel1, xv_next);
-        }
-        // ---- 2. vals of tile g
+        // ---- 1. operands: cols of tile g+1 (its gathers go out below) and vals of tile g, both from the ring
         const int32_t ts = w_tile * TILE;
         const int32_t p0 = ts + q * QUARTER + l; // my element of step TB*q of the tile; next step: +8
+        uint32_t ci[TB];
+        if (nel1 > 0) {
+            mbar_wait(bar0 + 8u * (sidx ^ 1u), ((g + 1u) >> 1) & 1u);
+            const uint32_t* sc = reinterpret_cast<const uint32_t*>(s_stream + w * G::WARP_SMEM +
+                                                                   (sidx ^ 1u) * G::STAGE_BYTES + TILE * 8) +
+                                 q * QUARTER + l;
+            if (nel1 == TILE) {
+#pragma unroll
+                for (int b = 0; b < TB; b++) ci[b] = sc[b * CVR_W];
+            } else {
+#pragma unroll
+                for (int b = 0; b < TB; b++) ci[b] = (q * QUARTER + l + b * CVR_W < nel1) ? sc[b * CVR_W] : 0u;
+            }
+        }
         double a[TB];
         {
             const double* sv =
@@ -613,12 +622,20 @@ cvr_spmv_pipe_kernel(const CvrChunk* __restrict__ chunks, int32_t T, int64_t nnz
                 for (int b = 0; b < TB; b++) a[b] = (q * QUARTER + l + b * CVR_W < nel0) ? sv[b * CVR_W] : 0.0;
             }
         }
-        // ---- 3. stage `sidx` is free (cols read one iteration ago, vals just now): refill it with tile
-        // g+2.  The refill is an async-proxy write to memory these generic-proxy loads just read:
-        // fence in every reader, converge, then re-arm.
+        // ---- 2. stage `sidx` is free (cols read one iteration ago, vals just now): refill it with tile
+        // g+2.  The refill is an async-proxy write to memory these generic-proxy loads just read: fence in
+        // every reader, converge, then re-arm.  The fence (MEMBAR + FENCE.VIEW.ASYNC) waits for every
+        // memory operation of the thread that is still in flight, so it has to sit BEFORE the gathers go
+        // out -- behind them it would wait for them and serialise the pipeline (ncu: 8 % of the stall
+        // samples of the first version, profiles/r02_prof_pipe9x4_v1_rmat24_source_top.txt).
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         nel2 = fetch_issue(sidx);
+        // ---- 3. gathers of tile g+1: in flight while tile g is walked
+        if (nel1 > 0) {
+#pragma unroll
+            for (int b = 0; b < TB; b++) xv_next[b] = __ldg(x + ci[b]);
+        }
 
         // ---- 4a. deliver the records of this tile to their owner threads
         for (;;) {
@@ -629,8 +646,10 @@ cvr_spmv_pipe_kernel(const CvrChunk* __restrict__ chunks, int32_t T, int64_t nnz
                 reinterpret_cast<unsigned char*>(&s_flags[w][b >> 2][owner])[b & 3u] = 1;
                 s_wb[w][b][owner] = held.y;
             }
-            const int32_t last = __shfl_sync(FULL, held.x, 31);
-            if ((uint32_t)last >= (uint32_t)(ts + TILE)) break; // batch reaches past the tile (or ended)
+            // records are sorted by position: the batch reaches past the tile (or the list ended, pos = -1)
+            // as soon as ANY lane holds a position beyond it -- a vote, not a shuffle round trip through
+            // the load/store queue the gathers occupy
+            if (__any_sync(FULL, (uint32_t)held.x >= (uint32_t)(ts + TILE))) break;
             rb += 32;
             held = nxt;
             nxt = (rb + 32 + t < n_rec) ? rec[rb + 32 + t] : make_int2(-1, 0);
@@ -679,19 +698,25 @@ cvr_spmv_pipe_kernel(const CvrChunk* __restrict__ chunks, int32_t T, int64_t nnz
             }
         }
 
-        // ---- 4c. carry chain over the four walkers of my SIMD lane
+        // ---- 4c. carry chain over the four walkers of my SIMD lane.  Walker r hands on
+        // out_r = has_r ? tail_r : cin_r + head_r, cin_r = out_(r-1), cin_0 = the lane's carry from the
+        // previous tile.  With v_r = has_r ? tail_r : head_r that is out_r = v_r + (has_r ? 0 : cin_r): every
+        // thread fetches the three other v of its SIMD lane with INDEPENDENT shuffles (they pipeline through
+        // the load/store queue; the dependent shuffle chain of round 1 cost three queue round trips) and the
+        // has-flags with one vote, then folds the chain locally.
         const bool has = mask != 0u;
-        double cin = (q == 0) ? lane_carry : 0.0;
-        double out = has ? tailsum : cin + head;
+        const unsigned has_all = __ballot_sync(FULL, has);
+        const double v_mine = has ? tailsum : head;
+        double vq[4];
 #pragma unroll
-        for (int r = 1; r < 4; r++) {
-            const double prev = __shfl_up_sync(FULL, out, CVR_W);
-            if (q == r) {
-                cin = prev;
-                out = has ? tailsum : cin + head;
-            }
+        for (int r = 0; r < 4; r++) vq[r] = __shfl_sync(FULL, v_mine, r * CVR_W + l);
+        double run = lane_carry, cin = lane_carry; // run = out_(r-1) while folding
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (r == q) cin = run;
+            run = ((has_all >> (r * CVR_W + l)) & 1u) ? vq[r] : run + vq[r];
         }
-        lane_carry = __shfl_sync(FULL, out, 24 + l);
+        lane_carry = run;
         if (has) emit<kPublish>(cx, head + cin, p0 + b_first * CVR_W, s_wb[w][b_first][t], carry_slot);
         __syncwarp(); // slots are reused by the next tile's delivery
 
@@ -837,11 +862,16 @@ struct Variant {
 constexpr Variant VARIANTS[] = {
     {"tile", false, TB_TILE, CVR_TMA_BLOCKS},
     {"pipe9x4", true, 9, 4},
-    {"pipe9x5", true, 9, 5},
+    {"pipe7x4", true, 7, 4},
     {"pipe7x5", true, 7, 5},
-    {"pipe7x6", true, 7, 6},
+    {"pipe5x5", true, 5, 5},
     {"pipe5x6", true, 5, 6},
-    {"pipe5x8", true, 5, 8},
+    {"pipe9x3", true, 9, 3},
+    {"tile7x7", true, 7, 7},
+    {"tile7x8", true, 7, 8},
+    {"tile11x5", true, 11, 5},
+    {"tile13x4", true, 13, 4},
+    {"tile5x8", true, 5, 8},
 };
 constexpr int N_VARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
 #ifndef CVR_DEFAULT_VARIANT
@@ -876,6 +906,33 @@ cudaError_t launch_ex(K kernel, int blocks, int threads, int smem, cudaStream_t 
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// experimental geometries of the round-1 kernel (plain flavour only): "tile<T>x<B>"
+template <int TB, int NB>
+struct TileOps {
+    static int resident_blocks()
+    {
+        int blocks = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<TB, NB, false>, WARPS * 32,
+                                                          Geo<TB>::DYN_SMEM) != cudaSuccess)
+            return 0;
+        return blocks;
+    }
+    static cudaError_t launch(bool publish, int blocks, cudaStream_t stream, bool programmatic,
+                              const CvrChunk* chunks, int32_t T, int64_t, const double* vals,
+                              const int32_t* cols, const int32_t* record, const double* x, double* y,
+                              const CvrPublish& pub)
+    {
+        if (publish) return cudaErrorNotSupported;
+        return launch_ex(cvr_spmv_tile_kernel<TB, NB, false>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
+                         programmatic, chunks, T, vals, cols, record, x, y, pub);
+    }
+    static void preload()
+    {
+        cudaFuncAttributes a;
+        cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, false>);
+    }
+};
+
 // one entry per variant: occupancy query and launch, plain and publishing flavour
 template <int TB, int NB>
 struct PipeOps {
@@ -908,11 +965,16 @@ struct PipeOps {
 #define CVR_FOR_PIPE_VARIANT(v, expr)                   \
     switch (v) {                                        \
     case 1: { using P = PipeOps<9, 4>; expr; } break;   \
-    case 2: { using P = PipeOps<9, 5>; expr; } break;   \
+    case 2: { using P = PipeOps<7, 4>; expr; } break;   \
     case 3: { using P = PipeOps<7, 5>; expr; } break;   \
-    case 4: { using P = PipeOps<7, 6>; expr; } break;   \
+    case 4: { using P = PipeOps<5, 5>; expr; } break;   \
     case 5: { using P = PipeOps<5, 6>; expr; } break;   \
-    case 6: { using P = PipeOps<5, 8>; expr; } break;   \
+    case 6: { using P = PipeOps<9, 3>; expr; } break;   \
+    case 7: { using P = TileOps<7, 7>; expr; } break;   \
+    case 8: { using P = TileOps<7, 8>; expr; } break;   \
+    case 9: { using P = TileOps<11, 5>; expr; } break;  \
+    case 10: { using P = TileOps<13, 4>; expr; } break; \
+    case 11: { using P = TileOps<5, 8>; expr; } break;  \
     default: break;                                     \
     }
 
@@ -926,7 +988,7 @@ int variant_resident_blocks(int v)
     if (slot && *slot > 0) return *slot;
     int blocks = 0;
     if (!VARIANTS[v].pipe) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<TB_TILE, false>, WARPS * 32,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<TB_TILE, CVR_TMA_BLOCKS, false>, WARPS * 32,
                                                           Geo<TB_TILE>::DYN_SMEM) != cudaSuccess)
             blocks = 0;
     } else {
@@ -960,7 +1022,7 @@ void cvr_preload_spmv_kernels()
 {
     cudaFuncAttributes a;
     const int v = selected_variant();
-    if (!VARIANTS[v].pipe) cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB_TILE, false>);
+    if (!VARIANTS[v].pipe) cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB_TILE, CVR_TMA_BLOCKS, false>);
     else {
         CVR_FOR_PIPE_VARIANT(v, P::preload())
     }
@@ -1015,10 +1077,10 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, int64_t nnz, const
     cudaError_t e = cudaSuccess;
     if (!VARIANTS[v].pipe) {
         if (pub)
-            e = launch_ex(cvr_spmv_tile_kernel<TB_TILE, true>, pblocks, threads, Geo<TB_TILE>::DYN_SMEM, stream,
+            e = launch_ex(cvr_spmv_tile_kernel<TB_TILE, CVR_TMA_BLOCKS, true>, pblocks, threads, Geo<TB_TILE>::DYN_SMEM, stream,
                           programmatic, chunks, n_chunks, vals, cols, record, x, y, *publish);
         else
-            e = launch_ex(cvr_spmv_tile_kernel<TB_TILE, false>, pblocks, threads, Geo<TB_TILE>::DYN_SMEM, stream,
+            e = launch_ex(cvr_spmv_tile_kernel<TB_TILE, CVR_TMA_BLOCKS, false>, pblocks, threads, Geo<TB_TILE>::DYN_SMEM, stream,
                           programmatic, chunks, n_chunks, vals, cols, record, x, y, none);
     } else {
         CVR_FOR_PIPE_VARIANT(v, e = P::launch(pub, pblocks, stream, programmatic, chunks, n_chunks, nnz, vals, cols,

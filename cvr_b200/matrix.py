@@ -127,6 +127,19 @@ class CvrMatrix:
         _lib.check(self._lib.cvr_device_vectors(self._h, C.byref(x), C.byref(y)))
         return x.value, y.value
 
+    @property
+    def kernel_name(self) -> str:
+        """The sweep kernel variant CVR_SPMV_KERNEL selects right now ("pipe9x4", "tile", ...)."""
+        return self._lib.cvr_kernel_variant().decode()
+
+    def column_footprint(self, used_dev, stream: int = 0) -> None:
+        """used_dev[c] = 1 (uint8, n_cols+1 entries, pre-zeroed) for every column id this matrix touches."""
+        _lib.check(self._lib.cvr_column_footprint(self._h, _ptr(used_dev), int(stream)))
+
+    def check_async_error(self) -> None:
+        """Raises CvrError(CVR_ERR_STATE) if a peer flag barrier of this handle timed out."""
+        _lib.check(self._lib.cvr_check_async_error(self._h))
+
     def device_arrays(self):
         """Raw device addresses (vals, cols, record) of the converted matrix, for measurement tools."""
         v, c, r = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -81,6 +81,8 @@ typedef struct cvr_info {
     double create_seconds;   /* upload + conversion, host wall clock */
     int64_t kernel_launches; /* kernels this handle has launched so far */
     int64_t device_bytes;    /* device memory owned by the handle */
+    double convert_kernel_seconds; /* the schedule + permute kernels alone (CUDA events; what B_conv is held against) */
+    double row_lists_seconds;      /* building the clear lists after them (host clock: it allocates and synchronises) */
 } cvr_info_t;
 
 /* CSR owned by the library, produced by cvr_read_matrix_market. */
@@ -218,6 +220,9 @@ int cvr_get_info(cvr_handle_t* h, cvr_info_t* info);
 /* Device pointers of the handle's x / y scratch vectors (n_cols+1 / n_rows+1
  * doubles), for callers that iterate on the device. */
 int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev);
+
+/* Name of the sweep kernel variant in use ("pipe9x4", "tile", ...; CVR_SPMV_KERNEL selects). */
+const char* cvr_kernel_variant(void);
 
 /* Device pointers of the converted matrix itself (read-only views, valid until cvr_destroy):
  * vals [nnz] f64, cols [nnz] i32 in CVR order, record [record_ints] i32.  For tools that run their

@@ -11,6 +11,8 @@
 //     variant 3: as 2, gather with L1::no_allocate
 //     variant 4: as 2, stream through cp.async.bulk (TMA) into shared memory, as the sweep does
 //     variant 5: as 2, gathers of tile k+1 issued before the FMAs of tile k (software pipeline)
+//     variant 6: as 2, every warp walks a contiguous chunk (probe_set_chunk) -- the sweep's access pattern
+//     variant 7 (probe_hot_run): as 2 plus a shared-memory cache of the hottest x entries
 //   U = elements (gathers in flight) per thread and pass: 4, 9 or 18.
 //   col_mask != 0: column &= col_mask  (shrinks the x footprint, e.g. to an L2-resident window)
 #include <cuda_runtime.h>
@@ -18,6 +20,8 @@
 #include <stdio.h>
 
 namespace {
+
+int g_chunk_el = 4032; // variant 6: elements per contiguous chunk (multiple of every tile size)
 
 __device__ __forceinline__ int32_t ld_stream_s32(const int32_t* p)
 {
@@ -212,6 +216,40 @@ probe_pipe_kernel(const int32_t* __restrict__ cols, const double* __restrict__ v
     if (acc == 123.456) out[0] = acc;
 }
 
+// variant 6: as 2, but every warp walks a CONTIGUOUS chunk of `chunk_el` elements tile by tile and
+// strides over chunks (chunk = warp, warp + n_warps, ...) -- the sweep's access pattern: n_warps
+// concurrent streams that are chunk_el * 12 bytes apart instead of one compact front
+template <int U>
+__global__ void __launch_bounds__(128)
+probe_chunked_kernel(const int32_t* __restrict__ cols, const double* __restrict__ vals, int64_t n,
+                     const double* __restrict__ x, double* __restrict__ out, uint32_t col_mask, int chunk_el)
+{
+    constexpr int TILE = 32 * U;
+    const int t = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_chunks = n / chunk_el;
+    const int tiles_per_chunk = chunk_el / TILE;
+    double acc = 0.0;
+    for (int64_t chunk = warp0; chunk < n_chunks; chunk += n_warps) {
+        for (int k = 0; k < tiles_per_chunk; k++) {
+            const int64_t base = chunk * chunk_el + (int64_t)k * TILE + t;
+            uint32_t c[U];
+            double a[U], g[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                c[u] = (uint32_t)ld_stream_s32(cols + base + 32 * u);
+                a[u] = ld_stream_f64(vals + base + 32 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) g[u] = ld_gather(x + (col_mask ? (c[u] & col_mask) : c[u]));
+#pragma unroll
+            for (int u = 0; u < U; u++) fma_ordered(acc, a[u], g[u]);
+        }
+    }
+    if (acc == 123.456) out[0] = acc;
+}
+
 template <int VARIANT, int U>
 cudaError_t launch(const int32_t* cols, const double* vals, int64_t n, const double* x, double* out,
                    int grid, uint32_t col_mask, int carveout)
@@ -222,6 +260,10 @@ cudaError_t launch(const int32_t* cols, const double* vals, int64_t n, const dou
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (carveout >= 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
         k<<<grid, 128, smem>>>(cols, vals, n, x, out, col_mask);
+    } else if (VARIANT == 6) {
+        auto k = probe_chunked_kernel<U>;
+        if (carveout >= 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        k<<<grid, 128>>>(cols, vals, n, x, out, col_mask, g_chunk_el);
     } else if (VARIANT == 5) {
         auto k = probe_pipe_kernel<U>;
         if (carveout >= 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
@@ -245,11 +287,92 @@ cudaError_t dispatch(int variant, const int32_t* cols, const double* vals, int64
     case 3: return launch<3, U>(cols, vals, n, x, out, grid, col_mask, carveout);
     case 4: return launch<4, U>(cols, vals, n, x, out, grid, col_mask, carveout);
     case 5: return launch<5, U>(cols, vals, n, x, out, grid, col_mask, carveout);
+    case 6: return launch<6, U>(cols, vals, n, x, out, grid, col_mask, carveout);
     }
     return cudaErrorInvalidValue;
 }
 
 } // namespace
+
+
+// variant 7: as 2, plus a shared-memory cache of the K hottest x entries.  `cols` must be relabelled by
+// popularity (rank 0 = most frequent column; run_probe.py does it), so "hot" is simply c < K; in the
+// product the same effect needs a remapped copy of the column stream.  One block per SM slot, `threads`
+// threads each (the cache is per block): measures what the miss path gains when a fraction of the
+// gathers never reaches it.
+template <int U>
+__global__ void __launch_bounds__(1024)
+probe_hot_kernel(const int32_t* __restrict__ cols, const double* __restrict__ vals, int64_t n,
+                 const double* __restrict__ x, double* __restrict__ out, uint32_t hot_k)
+{
+    constexpr int TILE = 32 * U;
+    extern __shared__ __align__(16) double s_hot[];
+    for (uint32_t i = threadIdx.x; i < hot_k; i += blockDim.x) s_hot[i] = x[i];
+    __syncthreads();
+    const int t = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_tiles = n / TILE;
+    double acc = 0.0;
+    for (int64_t tile = warp0; tile < n_tiles; tile += n_warps) {
+        const int64_t base = tile * TILE + t;
+        uint32_t c[U];
+        double a[U], g[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            c[u] = (uint32_t)ld_stream_s32(cols + base + 32 * u);
+            a[u] = ld_stream_f64(vals + base + 32 * u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (c[u] < hot_k) g[u] = s_hot[c[u]];
+            else g[u] = ld_gather(x + c[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) fma_ordered(acc, a[u], g[u]);
+    }
+    if (acc == 123.456) out[0] = acc;
+}
+
+extern "C" int probe_hot_run(int U, const int32_t* cols, const double* vals, int64_t n, const double* x,
+                             double* out, int blocks_per_sm, int threads, uint32_t hot_k, int reps, float* ms_out)
+{
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int smem = (int)hot_k * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaError_t e = cudaSuccess;
+    float best = 1e30f;
+    for (int r = 0; r < reps + 2 && e == cudaSuccess; r++) {
+        cudaEventRecord(e0);
+        if (U == 4) {
+            cudaFuncSetAttribute(probe_hot_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            probe_hot_kernel<4><<<sms * blocks_per_sm, threads, smem>>>(cols, vals, n, x, out, hot_k);
+        } else {
+            cudaFuncSetAttribute(probe_hot_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            probe_hot_kernel<9><<<sms * blocks_per_sm, threads, smem>>>(cols, vals, n, x, out, hot_k);
+        }
+        e = cudaGetLastError();
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) e = cudaGetLastError();
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "probe_hot_run: %s\n", cudaGetErrorString(e));
+        return -1;
+    }
+    *ms_out = best;
+    return 0;
+}
+
+extern "C" void probe_set_chunk(int chunk_el) { g_chunk_el = chunk_el; }
 
 extern "C" int probe_run(int variant, int U, const int32_t* cols, const double* vals, int64_t n,
                          const double* x, double* out, int blocks_per_sm, uint32_t col_mask,

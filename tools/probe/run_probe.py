@@ -27,11 +27,18 @@ def build():
                            "-Xcompiler", "-fPIC", "-Xptxas", "-O1", "-shared", "-o", LIB, src])
 
 
+class _Raw:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="rmat24,web")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "probe.jsonl"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only-chunked", action="store_true")
+    ap.add_argument("--hot", action="store_true", help="only the hot-x cache experiment (variant 7)")
     args = ap.parse_args()
     build()
     import torch
@@ -88,8 +95,55 @@ def main():
                     if variant == 5 and U == 18 and blocks > 6:
                         continue  # 2 x 18 x (8+8) bytes of registers per thread
                     grid.append((variant, U, blocks))
+        if args.hot:
+            # relabel columns by popularity: rank 0 = most frequent
+            ncol = n_cols + 1
+            cview = torch.as_tensor(_Raw(cols, nnz, "<i4"), device=dev)
+            counts = torch.bincount(cview.long(), minlength=ncol)
+            order = torch.argsort(counts, descending=True)
+            rank = torch.empty(ncol, dtype=torch.int32, device=dev)
+            rank[order] = torch.arange(ncol, dtype=torch.int32, device=dev)
+            cols_perm = rank[cview.long()].contiguous()
+            csum = torch.cumsum(counts[order].double(), 0) / float(nnz)
+            lib.probe_hot_run.restype = C.c_int
+            lib.probe_hot_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
+            for hot_k in (0, 1024, 4096, 8192, 16384, 24576):
+                for U, blocks, threads in ((9, 1, 512), (9, 1, 768), (9, 1, 1024), (4, 1, 1024), (9, 2, 384), (9, 2, 512)):
+                    if hot_k * 8 * blocks > 200 * 1024:
+                        continue
+                    best = 1e30
+                    for _ in range(3 if flush is not None else 1):
+                        if flush is not None:
+                            flush.fill_(1)
+                        ms = C.c_float()
+                        rc = lib.probe_hot_run(U, cols_perm.data_ptr(), vals, nnz, x.data_ptr(), out.data_ptr(), blocks,
+                                               threads, hot_k, 1 if flush is not None else 3, C.byref(ms))
+                        if rc == 0:
+                            best = min(best, ms.value)
+                    rec = {"workload": name, "variant": 7, "U": U, "blocks_per_sm": blocks, "threads": threads,
+                           "warps_per_sm": blocks * threads // 32, "hot_k": hot_k,
+                           "hot_hit_fraction": float(csum[hot_k - 1]) if hot_k else 0.0, "us": best * 1e3,
+                           "elem_per_clk_per_sm": nnz / (best * 1e-3) / (sm_mhz * 1e6) / sms}
+                    line = json.dumps(rec)
+                    print(line, flush=True)
+                    fout.write(line + "\n")
+                    fout.flush()
+            m.close()
+            del x, out, flush, cols_perm
+            torch.cuda.empty_cache()
+            continue
+        if args.only_chunked:
+            grid = [(2, 9, 6), (2, 9, 8)]
         for variant, U, blocks in grid:
             run(variant, U, blocks)
+        # the sweep's access pattern: every warp streams its own contiguous chunk
+        for chunk_el in (4032, 1152):  # multiples of 32*4, 32*9, 32*18
+            lib.probe_set_chunk(chunk_el)
+            for U, blocks in ((9, 6), (9, 8), (18, 4)):
+                r = run(6, U, blocks)
+                if r:
+                    r["chunk_el"] = chunk_el
         # x shrunk to an L2-resident window: separates "x misses L2" from "L1/L2 request rate"
         for mask in ((1 << 20) - 1, (1 << 14) - 1):
             for variant, U, blocks in ((2, 9, 8), (2, 18, 8), (4, 9, 6)):
