@@ -351,7 +351,7 @@ def single_gpu_measurement(name, args, dev, local_rank, peak, clocks, want_cuspa
         "l2": "inputs exceed L2 (no flush)" if flush is None else "L2 flushed between steps (384 MB write, untimed)",
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_TRAFFIC.get(name), "traffic_source": NCU_TRAFFIC_SOURCE.get(name),
-                     "kernel": "cvr_spmv_%s_kernel" % ("tile" if m.kernel_name == "tile" else "pipe"),
+                     "kernel": "cvr_spmv_tile_kernel",
                      "kernel_variant": m.kernel_name, "kernel_us": kernel_s * 1e6,
                      "algorithmic_bytes_per_launch": info["algorithmic_bytes"],
                      "kernel_share_of_step": kernel_s * 1e3 / ms_per_step,
@@ -643,7 +643,7 @@ def run_multi(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": 8 * (n_rows_total + world), "steps": e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "traffic_source": None, "peak_source": peak_src,
-                         "kernel": "cvr_spmv_%s_kernel (rank 0 shard)" % ("tile" if m.kernel_name == "tile" else "pipe"),
+                         "kernel": "cvr_spmv_tile_kernel (rank 0 shard)",
                          "kernel_variant": m.kernel_name, "kernel_us": kernel_s * 1e6,
                          "algorithmic_bytes_per_launch": shard_bytes, "x_entries_touched": x_touched,
                          "kernel_share_of_step": kernel_s * 1e3 / ms_per_step,

@@ -5,7 +5,7 @@ Python here is plumbing: ctypes over include/cvr_b200.h.  The product is libcvr_
 """
 from ._lib import CvrError, load as load_library  # noqa: F401
 from .csr import CsrMatrix, read_matrix, write_mtx  # noqa: F401
-from .matrix import CvrMatrix, DeviceCsr, pre_processing, spmv_compute_kernel, verify_csr  # noqa: F401
+from .matrix import CvrMatrix, DeviceCsr, ShardedCvr, pre_processing, spmv_compute_kernel, verify_csr  # noqa: F401
 
 __all__ = ["CvrError", "load_library", "CsrMatrix", "read_matrix", "write_mtx", "CvrMatrix",
-           "DeviceCsr", "pre_processing", "spmv_compute_kernel", "verify_csr"]
+           "DeviceCsr", "ShardedCvr", "pre_processing", "spmv_compute_kernel", "verify_csr"]

@@ -48,6 +48,15 @@ class CvrHostCsr(C.Structure):  # cvr_host_csr_t
                 ("row_delim32", c_int32_p), ("row_delim64", c_int64_p)]
 
 
+class CvrShardedInfo(C.Structure):  # cvr_sharded_info_t
+    _fields_ = [("n_parts", C.c_int32), ("exchange", C.c_int32),
+                ("n_rows", C.c_int64), ("n_cols", C.c_int64), ("nnz", C.c_int64),
+                ("device", C.c_int32 * 8), ("row_begin", C.c_int64 * 8), ("row_end", C.c_int64 * 8),
+                ("part_nnz", C.c_int64 * 8), ("part_chunks", C.c_int32 * 8), ("peer_bytes_per_iter", C.c_int64 * 8),
+                ("create_seconds", C.c_double), ("convert_seconds", C.c_double), ("kernel_launches", C.c_int64)]
+
+
+SHARD_PEER, SHARD_NCCL, SHARD_DENSE = 0, 1, 2
 MM_REF_LAST_DELIM = 1
 MM_KEEP_LAST_LINE = 2
 
@@ -74,6 +83,12 @@ SIGNATURES = {
     "cvr_peer_close": (C.c_int, [C.c_int, C.c_void_p]),
     "cvr_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
     "cvr_peer_barrier": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
+    "cvr_create_sharded": (C.c_int, [C.POINTER(CvrCsr), C.c_int32, C.POINTER(C.c_int), C.c_int, C.c_int,
+                                    C.POINTER(C.c_void_p)]),
+    "cvr_sharded_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_double_p]),
+    "cvr_sharded_get_info": (C.c_int, [C.c_void_p, C.POINTER(CvrShardedInfo)]),
+    "cvr_sharded_part": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "cvr_sharded_destroy": (None, [C.c_void_p]),
     "cvr_verify_csr": (C.c_int, [C.POINTER(CvrCsr), C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
                                 c_int64_p, c_double_p, c_int64_p]),
     "cvr_export": (C.c_int, [C.c_void_p, C.POINTER(CvrArrays)]),
@@ -81,7 +96,7 @@ SIGNATURES = {
     "cvr_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "cvr_get_info": (C.c_int, [C.c_void_p, C.POINTER(CvrInfo)]),
     "cvr_device_vectors": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
-    "cvr_kernel_variant": (C.c_char_p, []),
+    "cvr_kernel_variant": (C.c_char_p, [C.c_void_p]),
     "cvr_device_arrays": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cvr_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "cvr_get_kernel_timing": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),

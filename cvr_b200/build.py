@@ -16,7 +16,7 @@ BIN_DIR = os.path.join(PKG, "bin")
 LIB = os.path.join(LIB_DIR, "libcvr_b200.so")
 CLI = os.path.join(BIN_DIR, "spmv.cvr")
 
-CUDA_SOURCES = ["cvr_api.cu", "cvr_convert.cu", "cvr_spmv.cu", "cvr_check.cu", "cvr_mm_reader.cpp"]
+CUDA_SOURCES = ["cvr_api.cu", "cvr_convert.cu", "cvr_spmv.cu", "cvr_check.cu", "cvr_sharded.cu", "cvr_mm_reader.cpp"]
 CLI_SOURCES = ["cli/spmv_cvr_main.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -60,7 +60,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     extra = os.environ.get("CVR_NVCC_EXTRA", "").split()  # experiments, e.g. -DCVR_MIN_BLOCKS=8
-    log = _run([_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", LIB, *srcs, "-lgomp"], verbose)
+    log = _run([_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", LIB, *srcs, "-lgomp", "-ldl"], verbose)
     with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
         f.write(log)
     return LIB

@@ -9,8 +9,11 @@
 //   numThreads     number of CVR chunks (the reference's OpenMP thread count, so the
 //                  structure arrays are comparable at equal values); 0 = fill the device.
 //   numIterations  SpMVs to run and average, x = 1.0 like the reference (:1788).
-// Environment: CVR_DEVICE (default 0), CVR_MM_REF_LAST_DELIM=1, CVR_MM_KEEP_LAST_LINE=1,
-//              CVR_CHUNK_NNZ (auto chunk sizing, see cvr_auto_chunks).
+// Environment: CVR_DEVICE (default 0), or CVR_DEVICES=0,1,2,3 to row-shard the matrix by nnz over several
+//              GPUs (one process, cvr_create_sharded; numThreads is then the chunk count PER GPU);
+//              CVR_ITERATE=1 feeds y back into x every iteration (x <- A x, square matrices; one exchange
+//              per iteration over NVLink peer memory, CVR_EXCHANGE=nccl for the NCCL all-gather);
+//              CVR_MM_REF_LAST_DELIM=1, CVR_MM_KEEP_LAST_LINE=1, CVR_CHUNK_NNZ (auto chunk sizing).
 //
 // Differences from the reference, all visible on stdout:
 //   * the Throughput line reports 2*nnz/t (true nnz) and says so; the reference prints
@@ -24,7 +27,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
+#include <string>
 #include <vector>
 
 using std::cout;
@@ -42,6 +47,25 @@ static int env_int(const char* name, int dflt)
     return (s && *s) ? atoi(s) : dflt;
 }
 
+// CVR_DEVICES="0,1,2" -> {0, 1, 2}; empty when unset
+static std::vector<int> env_devices()
+{
+    std::vector<int> out;
+    const char* s = getenv("CVR_DEVICES");
+    if (!s || !*s) return out;
+    std::string tok;
+    for (const char* p = s;; p++) {
+        if (*p == ',' || *p == 0) {
+            if (!tok.empty()) out.push_back(atoi(tok.c_str()));
+            tok.clear();
+            if (*p == 0) break;
+        } else {
+            tok.push_back(*p);
+        }
+    }
+    return out;
+}
+
 [[noreturn]] static void die(const char* what)
 {
     std::cerr << what << ": " << cvr_last_error() << std::endl;
@@ -57,7 +81,11 @@ int main(int argc, char** argv)
     char* filename = argv[1];
     int n_chunks = atoi(argv[2]);
     const double n_times = atoi(argv[3]);
-    const int device = env_int("CVR_DEVICE", 0);
+    const std::vector<int> devices = env_devices();
+    const int device = devices.empty() ? env_int("CVR_DEVICE", 0) : devices[0];
+    const bool sharded = devices.size() > 1;
+    const bool iterate = env_int("CVR_ITERATE", 0) != 0;
+    const double t_start = now_seconds();
 
     cout << "===========================================================================" << endl;
     cout << "=========*********            Input Arguments           *********==========" << endl;
@@ -82,6 +110,7 @@ int main(int argc, char** argv)
         return 1;
     }
     const double t_read = now_seconds() - t_read0;
+    const double t_ingested = now_seconds();
 
     cout << "===========================================================================" << endl;
     cout << "=========*********  Informations of the sparse matrix   *********==========" << endl;
@@ -115,6 +144,7 @@ int main(int argc, char** argv)
         y_check[(size_t)r] = sum;
         y_mag[(size_t)r] = mag;
     }
+    const double t_checked = now_seconds();
 
     cout << "===========================================================================" << endl;
     cout << "=========*********   Converting (CSR->CVR)      *********==========" << endl;
@@ -128,31 +158,83 @@ int main(int argc, char** argv)
     csr.row_delim32 = m.row_delim32;
     csr.row_delim64 = m.row_delim64;
     cvr_handle_t* h = nullptr;
-    if (cvr_create(&csr, n_chunks, device, &h) != CVR_OK) die("cvr_create");
-    cvr_info_t info;
-    cvr_get_info(h, &info);
-    n_chunks = info.n_chunks;
-    cout << "The Pre-processing(CSR->CVR)   Time of CVR   is " << info.create_seconds
+    cvr_sharded_t* sh = nullptr;
+    double create_seconds = 0.0, convert_seconds = 0.0;
+    int64_t algorithmic_bytes = 0;
+    if (!sharded) {
+        if (cvr_create(&csr, n_chunks, device, &h) != CVR_OK) die("cvr_create");
+        cvr_info_t info;
+        cvr_get_info(h, &info);
+        n_chunks = info.n_chunks;
+        create_seconds = info.create_seconds;
+        convert_seconds = info.convert_kernel_seconds;
+        algorithmic_bytes = info.algorithmic_bytes;
+    } else {
+        int flags = CVR_SHARD_PEER;
+        const char* ex = getenv("CVR_EXCHANGE");
+        if (ex && strcmp(ex, "nccl") == 0) flags = CVR_SHARD_NCCL;
+        if (cvr_create_sharded(&csr, n_chunks, devices.data(), (int)devices.size(), flags, &sh) != CVR_OK)
+            die("cvr_create_sharded");
+        cvr_sharded_info_t si;
+        cvr_sharded_get_info(sh, &si);
+        n_chunks = si.part_chunks[0];
+        create_seconds = si.create_seconds;
+        convert_seconds = si.convert_seconds;
+    }
+    cout << "The Pre-processing(CSR->CVR)   Time of CVR   is " << create_seconds
          << " seconds.   [file: " << filename << "] [threads: " << n_chunks << "]" << endl;
-    cout << "   (host->device upload + device conversion; conversion kernels alone: "
-         << info.convert_seconds << " seconds, " << n_chunks << " chunks on GPU " << device << ")" << endl;
+    if (!sharded)
+        cout << "   (host->device upload + device conversion; conversion kernels alone: " << convert_seconds
+             << " seconds, " << n_chunks << " chunks on GPU " << device << ")" << endl;
+    else {
+        cvr_sharded_info_t si;
+        cvr_sharded_get_info(sh, &si);
+        cout << "   (row shards by nnz over " << si.n_parts << " GPUs, " << n_chunks << " chunks each:";
+        for (int g = 0; g < si.n_parts; g++)
+            cout << " [GPU " << si.device[g] << ": rows " << si.row_begin[g] << ".." << si.row_end[g] - 1 << ", "
+                 << si.part_nnz[g] << " nnz]";
+        cout << "; exchange: " << (si.exchange ? "NCCL all-gather" : "fused peer stores") << ")" << endl;
+    }
     cout << endl;
+    const double t_created = now_seconds();
 
     cout << "===========================================================================" << endl;
     cout << "=========*********   SpMV Executes for " << n_times << " iterations    *********==========" << endl;
     cout << endl;
     const int iters = n_times >= 1 ? (int)n_times : 1;
     double secs = 0.0;
-    // one untimed pass: first-launch overhead is not part of the average
-    if (cvr_spmv(h, x.data(), y.data(), 1, nullptr) != CVR_OK) die("cvr_spmv");
-    if (cvr_spmv(h, x.data(), y.data(), iters, &secs) != CVR_OK) die("cvr_spmv");
+    // one untimed pass: first-launch overhead is not part of the average; it is also the pass the
+    // self-check looks at (one SpMV of x = 1, like the reference's verdict)
+    if (!sharded) {
+        if (cvr_spmv(h, x.data(), y.data(), 1, nullptr) != CVR_OK) die("cvr_spmv");
+    } else {
+        if (cvr_sharded_spmv(sh, x.data(), y.data(), 1, iterate ? 1 : 0, nullptr) != CVR_OK) die("cvr_sharded_spmv");
+    }
+    std::vector<double> y_timed((size_t)m.n_rows + 1, 0.0);
+    if (!sharded && !iterate) {
+        if (cvr_spmv(h, x.data(), y_timed.data(), iters, &secs) != CVR_OK) die("cvr_spmv");
+    } else if (!sharded) {
+        // x <- A x on one GPU: the library's sharded host with a single part swaps the two x buffers
+        const int one[1] = {device};
+        if (cvr_create_sharded(&csr, n_chunks, one, 1, CVR_SHARD_PEER, &sh) != CVR_OK) die("cvr_create_sharded");
+        if (cvr_sharded_spmv(sh, x.data(), y_timed.data(), iters, 1, &secs) != CVR_OK) die("cvr_sharded_spmv");
+    } else {
+        if (cvr_sharded_spmv(sh, x.data(), y_timed.data(), iters, iterate ? 1 : 0, &secs) != CVR_OK)
+            die("cvr_sharded_spmv");
+    }
     cout << "The SpMV Execution Time of CVR    is " << secs << " seconds.   [file: " << filename
          << "] [threads: " << n_chunks << "]" << endl;
     cout << "         The Throughput of CVR    is " << 2.0 * (double)m.nnz_file / secs / 1e9
          << " GFlops.    [file: " << filename << "] [threads: " << n_chunks << "] [2*nnz/t]" << endl;
-    cout << "   (achieved " << (double)info.algorithmic_bytes / secs / 1e9
-         << " GB/s over " << info.algorithmic_bytes << " algorithmic bytes per SpMV; y zeroing is inside the timed region)" << endl;
+    if (!sharded)
+        cout << "   (achieved " << (double)algorithmic_bytes / secs / 1e9 << " GB/s over " << algorithmic_bytes
+             << " algorithmic bytes per SpMV; y zeroing is inside the timed region"
+             << (iterate ? "; x <- A x every iteration" : "") << ")" << endl;
+    else
+        cout << "   (" << devices.size() << " GPUs" << (iterate ? ", x <- A x with one exchange per iteration" : ", same x every iteration, no communication")
+             << "; host wall clock around the loop)" << endl;
     cout << endl;
+    const double t_ran = now_seconds();
     cout << "===========================================================================" << endl;
 
     // self-check (:1916-1938), extended to the last row and to the relative bound
@@ -173,7 +255,10 @@ int main(int argc, char** argv)
     cout << "   (max |y - y_csr| / sum|a*x| = " << worst_rel << ", bound 1e-12; rows failing abs 1e-3: "
          << wrong_abs << ", rel 1e-12: " << wrong_rel << ")" << endl;
 
-    cvr_destroy(h);
+    cout << "   (wall: start->ingest done " << t_ingested - t_start << " s, host CSR check " << t_checked - t_ingested
+         << " s, upload+convert " << t_created - t_checked << " s, SpMV runs " << t_ran - t_created << " s)" << endl;
+    if (sh) cvr_sharded_destroy(sh);
+    if (h) cvr_destroy(h);
     cvr_free_host_csr(&m);
     return (wrong_abs == 0 && wrong_rel == 0) ? 0 : 2;
 }

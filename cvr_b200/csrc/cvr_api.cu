@@ -59,6 +59,7 @@ struct cvr_handle {
     int device = 0;
     int64_t n_rows = 0, n_cols = 0, nnz = 0;
     int32_t n_chunks = 0;
+    int variant = 0; // sweep geometry picked for this matrix (cvr_pick_sweep_variant)
     int64_t record_ints = 0;
     int64_t n_records = 0;
     // device arrays (the CVR structure)
@@ -81,6 +82,10 @@ struct cvr_handle {
     // optional per-launch timing of the SpMV kernel alone (cvr_set_kernel_timing)
     unsigned int* done_counter = nullptr; // [0] last-block detection of the publish epilogue,
                                           // [1] epoch of the first peer barrier that timed out (0 = none)
+    // CUDA graph of GRAPH_UNROLL iterations of the host-facing loop (cvr_spmv with iters >> 1): captured once
+    cudaGraphExec_t loop_graph = nullptr;
+    int loop_graph_variant = -1; // sweep geometry the graph was captured with (CVR_SPMV_KERNEL can change it)
+    int64_t loop_graph_kernels = 0;
     bool timing = false;
     std::vector<cudaEvent_t> timing_events; // begin/end pairs, `timing_used` of them recorded
     size_t timing_used = 0;
@@ -88,6 +93,7 @@ struct cvr_handle {
     ~cvr_handle()
     {
         cudaSetDevice(device);
+        if (loop_graph) cudaGraphExecDestroy(loop_graph);
         cudaFree(vals);
         cudaFree(cols);
         cudaFree(record);
@@ -114,6 +120,33 @@ cudaError_t dev_alloc(cvr_handle* h, T** p, size_t count)
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
     if (e == cudaSuccess) h->device_bytes += (int64_t)bytes;
     return e;
+}
+
+// delimiter read that works for both widths (HOST pointers only)
+int64_t host_delim(const cvr_csr_t* csr, int64_t k)
+{
+    return csr->row_delim32 ? (int64_t)csr->row_delim32[k] : csr->row_delim64[k];
+}
+
+// Host CSR only: delimiters start at 0, never decrease, and end at nnz -- or at nnz-1, the reference
+// reader's off-by-one (spmv.cpp:522-526), which create_common repairs on the device copy.
+int check_host_delimiters(const cvr_csr_t* csr, bool* ref_last_delim)
+{
+    *ref_last_delim = false;
+    if (host_delim(csr, 0) != 0) return fail(CVR_ERR_INVALID, "row_delim[0] must be 0");
+    int64_t prev = 0;
+    for (int64_t k = 1; k <= csr->n_rows + 1; k++) {
+        const int64_t v = host_delim(csr, k);
+        if (v < prev) return fail(CVR_ERR_INVALID, "row_delim decreases at index %lld", (long long)k);
+        prev = v;
+    }
+    if (prev == csr->nnz) return CVR_OK;
+    if (prev == csr->nnz - 1) {
+        *ref_last_delim = true;
+        return CVR_OK;
+    }
+    return fail(CVR_ERR_INVALID, "row_delim[n_rows+1] = %lld must be nnz = %lld (or nnz-1, the reference reader's "
+                "trailing delimiter)", (long long)prev, (long long)csr->nnz);
 }
 
 int check_csr(const cvr_csr_t* csr, int32_t n_chunks)
@@ -148,12 +181,16 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
     CUDA_TRY(dev_alloc(h, &h->chunks, (size_t)T));
     CUDA_TRY(dev_alloc(h, &h->x, (size_t)h->n_cols + 1));
     CUDA_TRY(dev_alloc(h, &h->y, (size_t)h->n_rows + 1));
+    // counters of the multi-GPU epilogue: allocated here, not lazily inside the iteration loop (an allocation
+    // or memset issued while a peer already spins at the flag barrier may have to wait for it)
+    CUDA_TRY(dev_alloc(h, &h->done_counter, 2));
+    CUDA_TRY(cudaMemsetAsync(h->done_counter, 0, 2 * sizeof(unsigned int), h->stream));
 
     int2* segments = nullptr;
     int32_t* seg_count = nullptr;
     const size_t seg_entries = (size_t)CVR_SEG_STRIDE * T + (size_t)h->n_rows + 64;
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&segments), sizeof(int2) * seg_entries));
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&seg_count), sizeof(int32_t) * (2 * (size_t)T + 2)); // + wide-chunk list
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&seg_count), sizeof(int32_t) * ((size_t)T + 2));
     if (e != cudaSuccess) {
         cudaFree(segments);
         return fail(CVR_ERR_CUDA, "cudaMalloc(seg_count): %s", cudaGetErrorString(e));
@@ -224,6 +261,35 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
     return CVR_OK;
 }
 
+int auto_chunks_for(int64_t nnz, int device, int variant, int32_t* n_chunks)
+{
+    if (!n_chunks || nnz < 16) return fail(CVR_ERR_INVALID, "bad arguments to cvr_auto_chunks");
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
+        return fail(CVR_ERR_CUDA, "cannot query device %d: no CPU fallback", device);
+    // One warp per chunk, chunks are nnz-balanced: size the count in whole WAVES of resident
+    // warps (SMs x warps the SpMV kernel keeps resident per SM) so the last wave is full, and
+    // aim at ~4K elements (48 KB of stream) per chunk: the per-chunk prologue (descriptor -> records ->
+    // first bulk copy, a chain of dependent loads) costs ~2 us of a warp, measured as FEM 69.7 us at
+    // 14208 chunks vs 64.1-64.8 us at 3552-7104; skewed matrices want more, smaller chunks for balance
+    // (R-MAT-22: 322 us at 21312 chunks vs 346 us at 7104), 4K is the compromise.  CVR_CHUNK_NNZ overrides.
+    int64_t target_nnz = 4096;
+    if (const char* s = getenv("CVR_CHUNK_NNZ")) {
+        const long long v = atoll(s);
+        if (v >= 16) target_nnz = v;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return fail(CVR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    const int64_t wave = (int64_t)sms * cvr_spmv_resident_warps_per_sm(variant);
+    int64_t waves = (nnz / target_nnz + wave / 2) / wave;
+    if (waves < 1) waves = 1;
+    int64_t t = waves * wave;
+    if (t > nnz / 16) t = nnz / 16;
+    if (t > 0x3fffffff) t = 0x3fffffff;
+    if (t < 1) t = 1;
+    *n_chunks = (int32_t)t;
+    return CVR_OK;
+}
+
 int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_on_device,
                   cvr_handle_t** out)
 {
@@ -237,8 +303,9 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
     if (device < 0 || device >= n_dev)
         return fail(CVR_ERR_INVALID, "device %d out of range [0, %d)", device, n_dev);
     CUDA_TRY(cudaSetDevice(device));
+    const int variant = cvr_pick_sweep_variant(csr->nnz, csr->n_rows);
     if (n_chunks == 0) {
-        rc = cvr_auto_chunks(csr->nnz, device, &n_chunks);
+        rc = auto_chunks_for(csr->nnz, device, variant, &n_chunks);
         if (rc != CVR_OK) return rc;
     }
 
@@ -259,6 +326,7 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
     h->n_cols = csr->n_cols;
     h->nnz = csr->nnz;
     h->n_chunks = n_chunks;
+    h->variant = variant;
     h->record_ints = cvr_record_ints(csr->n_rows, n_chunks);
 
     cudaError_t e;
@@ -273,6 +341,34 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
     double* d_val = nullptr;
     int32_t* d_col = nullptr;
     void* d_rd = nullptr;
+    bool ref_last_delim = false;
+    if (!csr_on_device) {
+        rc = check_host_delimiters(csr, &ref_last_delim);
+        if (rc != CVR_OK) {
+            delete h;
+            return rc;
+        }
+    } else {
+        // device CSR: only the last delimiter is inspected (one 4/8-byte copy)
+        int64_t last = 0;
+        if (csr->row_delim64) {
+            e = cudaMemcpy(&last, csr->row_delim64 + csr->n_rows + 1, 8, cudaMemcpyDeviceToHost);
+        } else {
+            int32_t l32 = 0;
+            e = cudaMemcpy(&l32, csr->row_delim32 + csr->n_rows + 1, 4, cudaMemcpyDeviceToHost);
+            last = l32;
+        }
+        if (e != cudaSuccess) {
+            delete h;
+            return fail(CVR_ERR_CUDA, "cannot read row_delim[n_rows+1] from the device: %s", cudaGetErrorString(e));
+        }
+        if (last == csr->nnz - 1) ref_last_delim = true;
+        else if (last != csr->nnz) {
+            delete h;
+            return fail(CVR_ERR_INVALID, "row_delim[n_rows+1] = %lld must be nnz = %lld (or nnz-1)", (long long)last,
+                        (long long)csr->nnz);
+        }
+    }
     if (!csr_on_device) {
         const size_t rd_bytes = (size_t)(csr->n_rows + 2) * (csr->row_delim64 ? 8 : 4);
         if ((e = cudaMalloc(reinterpret_cast<void**>(&d_val), sizeof(double) * (size_t)csr->nnz)) == cudaSuccess &&
@@ -293,6 +389,33 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
         dev.col = d_col;
         dev.row_delim32 = csr->row_delim64 ? nullptr : static_cast<const int32_t*>(d_rd);
         dev.row_delim64 = csr->row_delim64 ? static_cast<const int64_t*>(d_rd) : nullptr;
+    } else if (ref_last_delim) {
+        // the caller's device CSR is read-only: repair a private copy of the delimiters
+        const size_t rd_bytes = (size_t)(csr->n_rows + 2) * (csr->row_delim64 ? 8 : 4);
+        if ((e = cudaMalloc(&d_rd, rd_bytes)) == cudaSuccess)
+            e = cudaMemcpy(d_rd, csr->row_delim64 ? (const void*)csr->row_delim64 : (const void*)csr->row_delim32,
+                           rd_bytes, cudaMemcpyDeviceToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d_rd);
+            delete h;
+            return fail(CVR_ERR_CUDA, "delimiter copy failed: %s", cudaGetErrorString(e));
+        }
+        dev.row_delim32 = csr->row_delim64 ? nullptr : static_cast<const int32_t*>(d_rd);
+        dev.row_delim64 = csr->row_delim64 ? static_cast<const int64_t*>(d_rd) : nullptr;
+    }
+    if (ref_last_delim) {
+        // trailing delimiters nnz-1 -> nnz (see cvr_launch_fix_last_delim): the converter then never looks
+        // for a row past the end, and no tail row n_rows+1 can reach the sweep
+        if (cvr_launch_fix_last_delim(csr->row_delim64 ? nullptr : static_cast<int32_t*>(d_rd),
+                                      csr->row_delim64 ? static_cast<int64_t*>(d_rd) : nullptr, csr->n_rows, csr->nnz,
+                                      h->stream) < 0 ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) {
+            cudaFree(d_val);
+            cudaFree(d_col);
+            cudaFree(d_rd);
+            delete h;
+            return fail(CVR_ERR_CUDA, "delimiter repair failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
     }
 
     rc = convert_on_device(h, &dev);
@@ -338,31 +461,8 @@ int64_t cvr_record_ints(int64_t n_rows, int32_t n_chunks)
 
 int cvr_auto_chunks(int64_t nnz, int device, int32_t* n_chunks)
 {
-    if (!n_chunks || nnz < 16) return fail(CVR_ERR_INVALID, "bad arguments to cvr_auto_chunks");
-    int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
-        return fail(CVR_ERR_CUDA, "cannot query device %d: no CPU fallback", device);
-    // One warp per chunk, chunks are nnz-balanced: size the count in whole WAVES of resident
-    // warps (SMs x warps the SpMV kernel keeps resident per SM) so the last wave is full, and
-    // aim at ~4K elements (48 KB of stream) per chunk: the per-chunk prologue (descriptor -> records ->
-    // first bulk copy, a chain of dependent loads) costs ~2 us of a warp, measured as FEM 69.7 us at
-    // 14208 chunks vs 64.1-64.8 us at 3552-7104; skewed matrices want more, smaller chunks for balance
-    // (R-MAT-22: 322 us at 21312 chunks vs 346 us at 7104), 4K is the compromise.  CVR_CHUNK_NNZ overrides.
-    int64_t target_nnz = 4096;
-    if (const char* s = getenv("CVR_CHUNK_NNZ")) {
-        const long long v = atoll(s);
-        if (v >= 16) target_nnz = v;
-    }
-    if (cudaSetDevice(device) != cudaSuccess) return fail(CVR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    const int64_t wave = (int64_t)sms * cvr_spmv_resident_warps_per_sm();
-    int64_t waves = (nnz / target_nnz + wave / 2) / wave;
-    if (waves < 1) waves = 1;
-    int64_t t = waves * wave;
-    if (t > nnz / 16) t = nnz / 16;
-    if (t > 0x3fffffff) t = 0x3fffffff;
-    if (t < 1) t = 1;
-    *n_chunks = (int32_t)t;
-    return CVR_OK;
+    // without the row count the short-row geometry is assumed (cvr_create knows the rows and may differ)
+    return auto_chunks_for(nnz, device, cvr_pick_sweep_variant(nnz, nnz), n_chunks);
 }
 
 int cvr_create(const cvr_csr_t* csr_host, int32_t n_chunks, int device, cvr_handle_t** out)
@@ -443,7 +543,7 @@ static int spmv_device_impl(cvr_handle_t* h, const double* x_dev, double* y_dev,
         ee = h->timing_events[h->timing_used + 1];
         h->timing_used += 2;
     }
-    const int launched = cvr_launch_spmv(h->chunks, h->n_chunks, h->nnz, h->vals, h->cols, h->record,
+    const int launched = cvr_launch_spmv(h->variant, h->chunks, h->n_chunks, h->vals, h->cols, h->record,
                                          x_dev, y_dev, h->n_rows, h->rows, pub,
                                          static_cast<cudaStream_t>(cuda_stream), eb, ee, bar,
                                          h->done_counter, y_is_clear);
@@ -461,8 +561,47 @@ int cvr_spmv(cvr_handle_t* h, const double* x_host, double* y_host, int32_t iter
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(h->x, x_host, sizeof(double) * (size_t)(h->n_cols + 1),
                              cudaMemcpyHostToDevice, h->stream));
+    // The iteration loop (the reference's spmv.cpp:1024-1034).  From GRAPH_UNROLL iterations on it is replayed
+    // from a CUDA graph captured once per handle: GRAPH_UNROLL x (clearing kernel -> sweep, programmatic edge
+    // kept) per graph launch instead of two launches per iteration.  CVR_NO_GRAPH=1 keeps the plain loop.
+    constexpr int32_t GRAPH_UNROLL = 20;
+    int32_t done = 0;
+    const char* ng = getenv("CVR_NO_GRAPH");
+    if (iters >= GRAPH_UNROLL && !h->timing && !(ng && *ng == '1')) {
+        const int variant_now = cvr_pick_sweep_variant(h->nnz, h->n_rows);
+        if (h->loop_graph && h->loop_graph_variant != variant_now) {
+            cudaGraphExecDestroy(h->loop_graph);
+            h->loop_graph = nullptr;
+        }
+        if (!h->loop_graph) {
+            cudaGraph_t graph = nullptr;
+            const int64_t l0 = h->launches;
+            cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+            int rc = CVR_OK;
+            if (ce == cudaSuccess) {
+                for (int32_t it = 0; it < GRAPH_UNROLL && rc == CVR_OK; it++)
+                    rc = cvr_spmv_device(h, h->x, h->y, h->stream);
+                ce = cudaStreamEndCapture(h->stream, &graph);
+            }
+            h->loop_graph_kernels = h->launches - l0;
+            h->launches = l0; // nothing ran yet
+            if (rc == CVR_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&h->loop_graph, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != CVR_OK || ce != cudaSuccess) {
+                cudaGetLastError(); // capture not possible here: fall back to the plain loop
+                h->loop_graph = nullptr;
+            }
+            h->loop_graph_variant = variant_now;
+        }
+    }
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    for (int32_t it = 0; it < iters; it++) {
+    if (h->loop_graph) {
+        for (; done + GRAPH_UNROLL <= iters; done += GRAPH_UNROLL) {
+            CUDA_TRY(cudaGraphLaunch(h->loop_graph, h->stream));
+            h->launches += h->loop_graph_kernels;
+        }
+    }
+    for (int32_t it = done; it < iters; it++) {
         const int rc = cvr_spmv_device(h, h->x, h->y, h->stream);
         if (rc != CVR_OK) return rc;
     }
@@ -538,7 +677,7 @@ int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev)
     return CVR_OK;
 }
 
-const char* cvr_kernel_variant(void) { return cvr_spmv_kernel_name(); }
+const char* cvr_kernel_variant(cvr_handle_t* h) { return cvr_spmv_kernel_name(h ? h->variant : 0); }
 
 int cvr_device_arrays(cvr_handle_t* h, const double** vals_dev, const int32_t** cols_dev,
                       const int32_t** record_dev)
@@ -757,6 +896,7 @@ int cvr_load(const char* path, int device, cvr_handle_t** out)
     h->n_cols = hd.n_cols;
     h->nnz = hd.nnz;
     h->n_chunks = hd.n_chunks;
+    h->variant = cvr_pick_sweep_variant(hd.nnz, hd.n_rows);
     h->record_ints = hd.record_ints;
     h->n_records = hd.n_records;
     h->rows.n_boundary = hd.n_boundary;
@@ -774,6 +914,8 @@ int cvr_load(const char* path, int device, cvr_handle_t** out)
         if ((e = dev_alloc(h, &h->rows.empty, (size_t)hd.n_empty + 1)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->x, (size_t)h->n_cols + 1)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->y, (size_t)h->n_rows + 1)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->done_counter, 2)) != cudaSuccess) break;
+        if ((e = cudaMemset(h->done_counter, 0, 2 * sizeof(unsigned int))) != cudaSuccess) break;
     } while (0);
     if (e != cudaSuccess) {
         fclose(f);

@@ -6,7 +6,7 @@
 // 8 values + 8 columns per step (:963-977).  Here the same greedy schedule is split
 // into two kernels:
 //
-//   cvr_schedule_kernel  one THREAD per chunk.  Event-driven restatement of the lane
+//   cvr_schedule_warp_kernel  one WARP per chunk.  Event-driven restatement of the lane
 //                        scheduler: instead of visiting every step it jumps from one
 //                        "a lane ran empty" event to the next (min over the 8 lane
 //                        counters).  Emits the reference's record / split / tail /
@@ -27,8 +27,6 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-constexpr int64_t WIDE_CHUNK_ROWS = 1024; // wider chunks are scheduled by a whole warp
-
 // largest m in [lo, hi] with rd[m] <= key (the bisection of spmv.cpp:637-650, :655-667)
 template <typename RdT>
 __device__ __forceinline__ int64_t last_row_not_after(const RdT* __restrict__ rd, int64_t lo,
@@ -43,203 +41,12 @@ __device__ __forceinline__ int64_t last_row_not_after(const RdT* __restrict__ rd
     return start - 1;
 }
 
-template <typename RdT>
-__global__ void __launch_bounds__(128)
-cvr_schedule_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int32_t T,
-                    int32_t* __restrict__ record, CvrChunk* __restrict__ chunks,
-                    int2* __restrict__ segments, int32_t* __restrict__ seg_count,
-                    int32_t* __restrict__ wide_list, int32_t* __restrict__ wide_count)
-{
-    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-
-    // nnz-balanced slice of this chunk, multiples of 16 (spmv.cpp:584-586, :615-627)
-    const int64_t per = (nnz / T / 16) * 16;
-    const int64_t brk = (nnz - per * T) / 16;
-    int64_t s, e;
-    if (t < brk) {
-        s = t * (per + 16);
-        e = (t + 1) * (per + 16);
-    } else {
-        s = t * per + brk * 16;
-        e = (t + 1) * per + brk * 16;
-    }
-    if (t == T - 1) e = nnz;
-
-    const int64_t r0 = last_row_not_after(rd, 0, n_rows, s);      // :631-650
-    int64_t r1 = last_row_not_after(rd, r0, n_rows, e - 1);       // :652-667
-    while (r1 <= n_rows && rd[r1 + 1] == rd[r1]) r1++;            // :687-688 (degenerate tails only)
-    const int64_t span = r1 - r0 + 1;
-    if (wide_list && span > WIDE_CHUNK_ROWS) {
-        // one thread pays ~1.4 us of dependent loads per row: a chunk that spans thousands of (mostly
-        // empty) rows would set the kernel's duration.  Hand it to cvr_schedule_warp_kernel.
-        wide_list[atomicAdd(wide_count, 1)] = t;
-        return;
-    }
-    const int32_t len = (int32_t)(e - s);
-    const int32_t n_steps = len / CVR_W;
-
-    int2* rec = reinterpret_cast<int2*>(record + cvr_record_offset(t, r0));
-    int2* seg = segments + cvr_segment_offset(t, r0);
-    int32_t n_rec = 0, n_seg = 0;
-
-    // lane trackers: vPack_valID / vPack_rowID / vPack_count / vPack_flag (:711-722)
-    int32_t src[CVR_W], row[CVR_W], left[CVR_W], from[CVR_W];
-    int64_t next_row = r0;
-#pragma unroll
-    for (int l = 0; l < CVR_W; l++) { // :727-759
-        if (next_row < r1) {
-            src[l] = (int32_t)((int64_t)rd[next_row] - s);
-            row[l] = (int32_t)next_row;
-            left[l] = (int32_t)(rd[next_row + 1] - rd[next_row]);
-        } else if (next_row == r1) {
-            src[l] = (int32_t)((int64_t)rd[next_row] - s);
-            row[l] = (int32_t)next_row;
-            left[l] = (int32_t)(e - (int64_t)rd[next_row]);
-        } else {
-            src[l] = row[l] = left[l] = 0;
-        }
-        if (l == 0) { // the first row may have begun in the previous chunk
-            src[0] = 0;
-            left[0] = (next_row == r1) ? len : (int32_t)((int64_t)rd[next_row + 1] - s);
-        }
-        from[l] = -1;
-        next_row++;
-    }
-
-    unsigned stolen = 0;  // first_flag (:796)
-    unsigned dirty = 0xffu; // lanes whose source offset was (re)set at the current step
-    bool tail_stored = false, stealing = false;
-    int32_t split0 = 0, split1 = 0;
-    int32_t tail[CVR_W];
-#pragma unroll
-    for (int l = 0; l < CVR_W; l++) tail[l] = 0;
-
-    int32_t i = 0;
-    while (i < n_steps) {
-        // ---- events of step i: every lane whose counter is 0, in lane order (:814-816).
-        // Every loop over the 8 lanes is unrolled and the one dynamic index (the steal victim) goes
-        // through select chains, so the trackers stay in registers (as local-memory arrays an event
-        // cost ~1.4 us of dependent L1 round trips).
-#pragma unroll
-        for (int l = 0; l < CVR_W; l++) {
-            if (left[l] != 0) continue;
-            const int32_t pos = i * CVR_W + l;
-            if (next_row <= r1) {
-                // feeding (:821-868)
-                if (row[l] == (int32_t)r0) {
-                    split0 = pos;
-                } else {
-                    rec[n_rec++] = make_int2(pos, row[l]);
-                }
-                while (rd[next_row + 1] == rd[next_row]) next_row++; // skip empty rows
-                const int64_t a0 = (int64_t)rd[next_row], a1 = (int64_t)rd[next_row + 1];
-                src[l] = (int32_t)(a0 - s);
-                row[l] = (int32_t)next_row;
-                left[l] = (int32_t)(a1 - a0);
-                if (next_row == r1) {
-                    if (split1 == 0) split1 = pos;
-                    left[l] = (int32_t)(e - a0);
-#pragma unroll
-                    for (int q = 0; q < CVR_W; q++) tail[q] = row[q];
-                    tail_stored = true;
-#pragma unroll
-                    for (int q = 0; q < CVR_W; q++)
-                        if (left[q] == 0) from[q] = 0; // :855-856
-                }
-                next_row++;
-            } else {
-                // stealing (:869-943): split the first lane that holds more than the average
-                int32_t total = 0;
-#pragma unroll
-                for (int q = 0; q < CVR_W; q++) total += left[q];
-                const int32_t ave = total / CVR_W;
-                int victim = CVR_W - 1;
-#pragma unroll
-                for (int q = CVR_W - 2; q >= 0; q--)
-                    if (left[q] > ave) victim = q;
-                if (!((stolen >> l) & 1u)) {
-                    if (!stealing) {
-                        if (split1 == 0) split1 = (span <= CVR_W) ? -1 : pos;
-#pragma unroll
-                        for (int q = 0; q < CVR_W; q++) tail[q] = row[q];
-                        tail_stored = true;
-                        stealing = true;
-                    }
-                    rec[n_rec++] = make_int2(pos, l);
-                    stolen |= 1u << l;
-                } else {
-                    rec[n_rec++] = make_int2(pos, from[l]); // :904-909, unreachable (SURVEY 8a-R2 note i)
-                }
-                int32_t vsrc = src[0];
-#pragma unroll
-                for (int q = 1; q < CVR_W; q++) vsrc = (victim == q) ? src[q] : vsrc;
-                from[l] = victim;
-                src[l] = vsrc;
-                row[l] = victim;
-                left[l] = ave;
-#pragma unroll
-                for (int q = 0; q < CVR_W; q++) {
-                    if (q == victim) { // (never lane l itself: a stealer holds exactly the average)
-                        left[q] -= ave;
-                        src[q] += ave;
-                    }
-                }
-                dirty |= 1u << victim;
-            }
-            dirty |= 1u << l;
-        }
-        // ---- one segment entry per lane that changed its source at this step
-#pragma unroll
-        for (int l = 0; l < CVR_W; l++)
-            if ((dirty >> l) & 1u) seg[n_seg++] = make_int2(i * CVR_W + l, src[l]);
-        dirty = 0;
-
-        // ---- jump to the next step at which some lane runs empty
-        int32_t m = left[0];
-#pragma unroll
-        for (int l = 1; l < CVR_W; l++) m = min(m, left[l]);
-        if (m <= 0 || m >= n_steps - i) break;
-#pragma unroll
-        for (int l = 0; l < CVR_W; l++) {
-            src[l] += m;
-            left[l] -= m;
-        }
-        i += m;
-    }
-
-    // the eight terminators written inside the last step (:982-999)
-#pragma unroll
-    for (int l = 0; l < CVR_W; l++) rec[n_rec + l] = make_int2(-1, from[l] == -1 ? l : from[l]);
-    // The reference leaves final_2 unwritten when a chunk never fed its last row nor stole
-    // (span <= 8 and all lanes end together); its kernel then reads garbage.  Store the
-    // intended rows instead.
-    if (!tail_stored) {
-#pragma unroll
-        for (int q = 0; q < CVR_W; q++) tail[q] = row[q];
-    }
-
-    CvrChunk c;
-    c.start = s;
-    c.len = len;
-    c.first_row = (int32_t)r0;
-    c.last_row = (int32_t)r1;
-    c.split0 = split0;
-    c.split1 = split1;
-    c.n_rec = n_rec;
-#pragma unroll
-    for (int q = 0; q < CVR_W; q++) c.tail[q] = tail[q];
-    chunks[t] = c;
-    seg_count[t] = n_seg;
-}
-
 // ---------------------------------------------------------------------------------------
-// cvr_schedule_warp_kernel -- the same greedy schedule, one WARP per chunk (default).
+// cvr_schedule_warp_kernel -- the greedy lane schedule of spmv.cpp:808-1000, one WARP per chunk.
 //
-// The thread-per-chunk kernel above is a chain of dependent global loads (row delimiters) per
-// row event: ~1.4 us per row, and the kernel lasts as long as its slowest thread -- 14.5 ms on
-// R-MAT-24 where chunks in the sparse tail span 10^4 rows (profiles/r01_v6_launches_rmat24.csv).
-// Here the warp keeps a 32-entry window of row delimiters in registers (one coalesced load per 32
+// (Round 1 also shipped a thread-per-chunk version: a chain of dependent global loads per row event,
+// ~1.4 us per row, 14.5 ms on R-MAT-24 against 2.6 ms here -- removed in round 2.)
+// The warp keeps a 32-entry window of row delimiters in registers (one coalesced load per 32
 // rows), finds the next non-empty row with a ballot, and the eight lane trackers live in lanes
 // 0..7; control flow is warp-uniform and follows the reference's lane order exactly.
 // ---------------------------------------------------------------------------------------
@@ -247,14 +54,11 @@ template <typename RdT>
 __global__ void __launch_bounds__(128)
 cvr_schedule_warp_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows, int32_t T,
                          int32_t* __restrict__ record, CvrChunk* __restrict__ chunks,
-                         int2* __restrict__ segments, int32_t* __restrict__ seg_count,
-                         const int32_t* __restrict__ wide_list, const int32_t* __restrict__ wide_count)
+                         int2* __restrict__ segments, int32_t* __restrict__ seg_count)
 {
     const int t = threadIdx.x & 31;
-    const int32_t n_work = wide_list ? *wide_count : T; // no list: every chunk
     const int32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int32_t work = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; work < n_work; work += n_warps) {
-    const int32_t chunk = wide_list ? wide_list[work] : work;
+  for (int32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < T; chunk += n_warps) {
     const bool is_lane = t < CVR_W;
 
     const int64_t per = (nnz / T / 16) * 16;
@@ -455,7 +259,7 @@ cvr_schedule_warp_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows
         c->n_rec = n_rec;
         seg_count[chunk] = n_seg;
     }
-  } // next wide chunk
+  } // next chunk of this warp
 }
 
 // One warp per chunk; thread `lane_id` owns CVR element 32k + lane_id of window k, i.e.
@@ -534,32 +338,72 @@ __global__ void cvr_mark_boundary_kernel(const CvrChunk* __restrict__ chunks, in
         if (c.tail[q] != 0) flags[c.tail[q]] = 1;
 }
 
-// pass 0 counts, pass 1 appends (order inside a list is irrelevant)
+// pass 0 counts, pass 1 appends (order inside a list is irrelevant).  A block covers COLLECT_ROWS
+// consecutive rows and reserves its share of each list with ONE atomic per list: per-warp atomics on the
+// two counters serialise in L2 (same address) -- 1 M of them took 123 ms on R-MAT-24's 16.7 M rows
+// (BENCH r02 first run, extra.convert.row_lists_ms), more than the whole conversion.
+constexpr int COLLECT_THREADS = 256, COLLECT_PER_THREAD = 8, COLLECT_ROWS = COLLECT_THREADS * COLLECT_PER_THREAD;
+
 template <typename RdT>
-__global__ void cvr_collect_rows_kernel(const RdT* __restrict__ rd, int64_t n_rows,
-                                        const unsigned char* __restrict__ flags,
-                                        int32_t* __restrict__ boundary, int32_t* __restrict__ empty,
-                                        int32_t* __restrict__ counters, int pass)
+__global__ void __launch_bounds__(COLLECT_THREADS)
+cvr_collect_rows_kernel(const RdT* __restrict__ rd, int64_t n_rows,
+                        const unsigned char* __restrict__ flags,
+                        int32_t* __restrict__ boundary, int32_t* __restrict__ empty,
+                        int32_t* __restrict__ counters, int pass)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool is_b = false, is_e = false;
-    if (r <= n_rows) {
-        is_b = r >= 1 && flags[r];
-        is_e = !is_b && (r == 0 || rd[r + 1] == rd[r]);
+    __shared__ int s_b[COLLECT_THREADS / 32], s_e[COLLECT_THREADS / 32];
+    __shared__ int s_base[2];
+    const int64_t row0 = (int64_t)blockIdx.x * COLLECT_ROWS + threadIdx.x; // my rows: row0 + k * COLLECT_THREADS
+    unsigned bits_b = 0, bits_e = 0;
+#pragma unroll
+    for (int k = 0; k < COLLECT_PER_THREAD; k++) {
+        const int64_t r = row0 + (int64_t)k * COLLECT_THREADS;
+        if (r <= n_rows) {
+            const bool is_b = r >= 1 && flags[r];
+            const bool is_e = !is_b && (r == 0 || rd[r + 1] == rd[r]);
+            bits_b |= (unsigned)is_b << k;
+            bits_e |= (unsigned)is_e << k;
+        }
     }
-    const unsigned mb = __ballot_sync(FULL, is_b), me = __ballot_sync(FULL, is_e);
-    const int lane = threadIdx.x & 31;
-    int base_b = 0, base_e = 0;
-    if (lane == 0) {
-        if (mb) base_b = atomicAdd(&counters[0], __popc(mb));
-        if (me) base_e = atomicAdd(&counters[1], __popc(me));
+    // block-wide exclusive scan of the per-thread counts: warp scan, then the warp totals
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int nb = __popc(bits_b), ne = __popc(bits_e);
+    int xb = nb, xe = ne;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ub = __shfl_up_sync(FULL, xb, o), ue = __shfl_up_sync(FULL, xe, o);
+        if (lane >= o) {
+            xb += ub;
+            xe += ue;
+        }
     }
-    if (pass == 1) {
-        base_b = __shfl_sync(FULL, base_b, 0);
-        base_e = __shfl_sync(FULL, base_e, 0);
-        const unsigned lt = (1u << lane) - 1u;
-        if (is_b) boundary[base_b + __popc(mb & lt)] = (int32_t)r;
-        if (is_e) empty[base_e + __popc(me & lt)] = (int32_t)r;
+    if (lane == 31) {
+        s_b[warp] = xb;
+        s_e[warp] = xe;
+    }
+    __syncthreads();
+    int wb = 0, we = 0, tb = 0, te = 0;
+#pragma unroll
+    for (int w = 0; w < COLLECT_THREADS / 32; w++) {
+        if (w < warp) {
+            wb += s_b[w];
+            we += s_e[w];
+        }
+        tb += s_b[w];
+        te += s_e[w];
+    }
+    if (threadIdx.x == 0) {
+        s_base[0] = tb ? atomicAdd(&counters[0], tb) : 0;
+        s_base[1] = te ? atomicAdd(&counters[1], te) : 0;
+    }
+    if (pass == 0) return;
+    __syncthreads();
+    int ob = s_base[0] + wb + xb - nb, oe = s_base[1] + we + xe - ne;
+#pragma unroll
+    for (int k = 0; k < COLLECT_PER_THREAD; k++) {
+        const int32_t r = (int32_t)(row0 + (int64_t)k * COLLECT_THREADS);
+        if ((bits_b >> k) & 1u) boundary[ob++] = r;
+        if ((bits_e >> k) & 1u) empty[oe++] = r;
     }
 }
 
@@ -568,8 +412,6 @@ __global__ void cvr_collect_rows_kernel(const RdT* __restrict__ rd, int64_t n_ro
 void cvr_preload_convert_kernels()
 {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, cvr_schedule_kernel<int32_t>);
-    cudaFuncGetAttributes(&a, cvr_schedule_kernel<int64_t>);
     cudaFuncGetAttributes(&a, cvr_schedule_warp_kernel<int32_t>);
     cudaFuncGetAttributes(&a, cvr_schedule_warp_kernel<int64_t>);
     cudaFuncGetAttributes(&a, cvr_permute_kernel);
@@ -588,8 +430,8 @@ int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t*
         return -1;
     }
     int launched = 0, rc = 0;
-    const int threads = 256;
-    const int row_blocks = (int)((n_rows + 1 + threads - 1) / threads);
+    const int threads = COLLECT_THREADS;
+    const int row_blocks = (int)((n_rows + 1 + COLLECT_ROWS - 1) / COLLECT_ROWS);
     do {
         cudaMemsetAsync(flags, 0, (size_t)n_rows + 2, stream);
         cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), stream);
@@ -629,44 +471,20 @@ int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t*
 int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream)
 {
     const int threads = 128;
-    // Scheduling: one warp per chunk (cvr_schedule_warp_kernel) by default.  CVR_SCHEDULE=thread runs the
-    // first-generation one-thread-per-chunk kernel, CVR_SCHEDULE=hybrid threads for ordinary chunks and
-    // warps for chunks spanning > WIDE_CHUNK_ROWS rows (the list lives in seg_count's tail: T + 1 extra
-    // ints).  Measured (ncu, cold): FEM 179 / 241 us, web 183 / 466 us, road 2.4 / 2.5 ms, R-MAT-24 2.6 / 14.5 ms
-    // (warp / thread); all modes are bit-exact.
-    static const int forced = [] {
-        const char* e = getenv("CVR_SCHEDULE");
-        if (e && strcmp(e, "thread") == 0) return 1;
-        if (e && strcmp(e, "hybrid") == 0) return 0;
-        return 2;
-    }();
-    int launched_sched = 0;
-    int32_t* wide_count = a.seg_count + a.n_chunks;
-    int32_t* wide_list = wide_count + 1;
-    if (forced != 2) {
-        const int sched_blocks = (a.n_chunks + threads - 1) / threads;
-        int32_t* wl = forced == 1 ? nullptr : wide_list;
-        if (wl && cudaMemsetAsync(wide_count, 0, sizeof(int32_t), stream) != cudaSuccess) return -1;
-        if (a.rd64)
-            cvr_schedule_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
-                a.rd64, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count, wl, wide_count);
-        else
-            cvr_schedule_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
-                a.rd32, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count, wl, wide_count);
-        launched_sched++;
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
-    if (forced != 1) {
-        const int64_t want = ((int64_t)a.n_chunks * 32 + threads - 1) / threads;
-        const int sched_blocks = (int)(want < 148 * 16 ? want : 148 * 16);
-        const int32_t* wl = forced == 2 ? nullptr : wide_list;
-        if (a.rd64)
-            cvr_schedule_warp_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
-                a.rd64, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count, wl, wide_count);
-        else
-            cvr_schedule_warp_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
-                a.rd32, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count, wl, wide_count);
-        launched_sched++;
-    }
+    const int64_t want = ((int64_t)a.n_chunks * 32 + threads - 1) / threads;
+    const int sched_blocks = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+    if (a.rd64)
+        cvr_schedule_warp_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
+            a.rd64, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+    else
+        cvr_schedule_warp_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
+            a.rd32, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
     if (cudaGetLastError() != cudaSuccess) return -1;
     const int64_t warps = a.n_chunks;
     const int perm_blocks = (int)((warps * 32 + threads - 1) / threads);
@@ -674,5 +492,29 @@ int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream)
                                                             a.seg_count, a.csr_val, a.csr_col,
                                                             a.cvr_vals, a.cvr_cols);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    return launched_sched + 1;
+    return 2;
+}
+
+// The reference's readMatrix leaves row_delim[k] = nnz-1 for every k after the last non-empty row
+// (spmv.cpp:522-526): the last row looks one element short and the trailing delimiter is not nnz.  The
+// reference only survives that by reading rowDelimiters[nRows+2] out of bounds (:687-688, :837).  When
+// the last delimiter is nnz-1 no entry exceeds it and the entries equal to it are exactly that trailing
+// run, so the repair is elementwise: nnz-1 -> nnz (the last non-empty row gets its element back -- what a
+// correct CSR holds whenever that row has at least two entries).
+namespace {
+template <typename RdT>
+__global__ void cvr_fix_last_delim_kernel(RdT* __restrict__ rd, int64_t n_entries, int64_t nnz)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_entries && (int64_t)rd[k] == nnz - 1) rd[k] = (RdT)nnz;
+}
+} // namespace
+
+int cvr_launch_fix_last_delim(int32_t* rd32, int64_t* rd64, int64_t n_rows, int64_t nnz, cudaStream_t stream)
+{
+    const int64_t n = n_rows + 2;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (rd64) cvr_fix_last_delim_kernel<int64_t><<<blocks, 256, 0, stream>>>(rd64, n, nnz);
+    else cvr_fix_last_delim_kernel<int32_t><<<blocks, 256, 0, stream>>>(rd32, n, nnz);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -48,6 +48,7 @@ struct CvrPublish {
     int32_t mode;                  // bit 0: per-row stores at emit instead of the coalesced per-chunk push (A/B)
                                    // bit 1: do not re-publish 0.0 for the never-written rows
                                    // bit 2: y IS this GPU's slice of the next x (no local copy; y[0] is foreign)
+                                   // bit 3: no programmatic dependent launches (two shards share one device)
     int64_t row_offset;            // global row = row_offset + local row
     const uint8_t* needs;          // needs[local row] bit p: destination p reads that x entry (NULL: all do)
     const uint8_t* chunk_any;      // chunk_any[t] != 0: some row of chunk t's range has a reader elsewhere (NULL: all)
@@ -97,8 +98,10 @@ int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t*
 
 // Launchers (each returns the number of kernels it launched, or <0 on launch failure)
 int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream);
+// repairs the reference's off-by-one trailing delimiters (nnz-1 -> nnz) in a DEVICE delimiter array we own
+int cvr_launch_fix_last_delim(int32_t* rd32, int64_t* rd64, int64_t n_rows, int64_t nnz, cudaStream_t stream);
 // ev_begin / ev_end (optional) bracket the SpMV kernel alone, after y has been cleared
-int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, int64_t nnz, const double* vals,
+int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const double* vals,
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
                     int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
                     cudaStream_t stream, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr,
@@ -111,10 +114,12 @@ int cvr_launch_chunk_needs(const CvrChunk* chunks, int32_t n_chunks, const uint8
                            cudaStream_t stream);
 int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used, cudaStream_t stream);
 
-// resident warps per SM of the SpMV kernel in use (sizes the automatic chunk count)
-int cvr_spmv_resident_warps_per_sm();
-// name of the sweep variant CVR_SPMV_KERNEL selects ("pipe9x4", "tile", ...)
-const char* cvr_spmv_kernel_name();
+// sweep geometry for a matrix (index into the variant table of cvr_spmv.cu; CVR_SPMV_KERNEL overrides)
+int cvr_pick_sweep_variant(int64_t nnz, int64_t n_rows);
+// resident warps per SM of that geometry (sizes the automatic chunk count)
+int cvr_spmv_resident_warps_per_sm(int variant);
+// its name ("tile7x7", "tile11x5", ...)
+const char* cvr_spmv_kernel_name(int variant);
 
 // force-load the kernels' module so the first timed call does not pay CUDA's lazy loading
 void cvr_preload_convert_kernels();

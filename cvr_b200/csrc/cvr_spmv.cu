@@ -5,18 +5,21 @@
 // (paper Alg. 4), including the steal-only chunks (split1 == -1) the
 // reference kernel mishandles.
 //
-// Two sweep kernels live in this file (CVR_SPMV_KERNEL = pipe | tile selects one per launch; both
-// pass the same parity suite, tests/test_gpu_parity.py runs it over both):
-//   cvr_spmv_tile_kernel   round 1: tile walker, vals/cols staged by the TMA engine, one tile in flight
-//                          per warp (profiles/r01_*)
-//   cvr_spmv_pipe_kernel   round 2, the default: the same walker, software-pipelined -- the x gathers
-//                          of tile k+1 are in flight while tile k is walked, the TMA ring runs two
-//                          tiles ahead and crosses chunk boundaries, record batches are prefetched
-//                          (profiles/r02_*).  <..., kPublish> variants additionally push finished
-//                          rows to peer GPUs for the iterated multi-GPU SpMV.
-// The first two generations of round 1 (a window kernel with a warp-wide segmented reduction and the
-// walker with LDG-streamed operands) were re-measured against these on B200 (profiles/
-// r02_kernel_ab_round1_generations.jsonl: never faster on any workload) and removed.
+// One sweep kernel, cvr_spmv_tile_kernel<TB, NB, kPublish>, in two geometries picked per matrix (see
+// cvr_pick_sweep_variant): TB = 7 steps per walker at 7 resident blocks per SM for short-row matrices,
+// TB = 11 at 5 blocks for long regular rows; <..., kPublish> additionally pushes finished rows to peer
+// GPUs for the iterated multi-GPU SpMV.  What was measured against it on B200 in round 2 and removed
+// again (never faster on any BASELINE workload; numbers under profiles/, code in the git history):
+//   * round 1's window kernel (warp-wide segmented reduction) and LDG-streamed walker
+//     (profiles/r02_kernel_ab_round1_generations.jsonl);
+//   * a software-pipelined walker -- x gathers of tile k+1 in flight while tile k is walked, TMA ring
+//     two tiles ahead and across chunk boundaries, record batches prefetched (commits 0d94e38, d52c6bb;
+//     profiles/r02_kernel_ab_pipe_v1.jsonl, r02_kernel_ab_pipe_v2.jsonl, ncu r02_prof_pipe*): 0-20 %
+//     SLOWER.  tools/probe shows why nothing of that kind can help: on matrices whose x gather misses L1
+//     an SM retires ~1 gathered element per clock at ANY occupancy or depth (the L1 miss path), and every
+//     further load/store-unit operation (shared-memory operands, flag delivery, shuffles, stores) queues
+//     in front of the same unit -- the sweep is bound by load/store-unit work per element, not by latency
+//     (profiles/r02_gather_probe_summary.txt).
 //
 // Common semantics.  One WARP owns one chunk (the reference: one OpenMP thread).  A record
 // (pos, wb) means "the accumulator of SIMD lane pos%8 is flushed before step pos/8"
@@ -194,9 +197,6 @@ __device__ __forceinline__ void fma_if(double& acc, double a, double x, uint32_t
 // flag bytes (0/1) of a 32-bit word -> 4-bit mask
 __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return ((w * 0x00204081u) >> 21) & 0xfu; }
 
-#ifndef CVR_TMA_BLOCKS
-#define CVR_TMA_BLOCKS 6
-#endif
 
 template <int TB, int NB, bool kPublish>
 __global__ void __launch_bounds__(WARPS * 32, NB)
@@ -420,338 +420,6 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
 }
 
 
-// ---------------------------------------------------------------------------------------
-// cvr_spmv_pipe_kernel -- the walker above, software-pipelined (round 2, the default).
-//
-// Why: tools/probe (profiles/r02_gather_probe_summary.txt) shows that on matrices whose x gather
-// misses L1 (R-MAT, web) one SM retires at most ~1 gathered element per clock however many warps or
-// loads are in flight -- the L1 miss path, not HBM, is the ceiling (R-MAT-24: 0.94 ms for "stream +
-// gather + FMA" against 1.40 ms for the round-1 sweep).  The round-1 sweep loses the difference in
-// DUTY CYCLE: a warp issues the 288 gathers of a tile, waits for them, and only then delivers
-// records, walks, emits and synchronises -- all of that with no gather of its own outstanding.
-// Here the warp keeps the miss path fed from one tile to the next:
-//   * the x gathers of tile g+1 are issued BEFORE tile g is walked (xv / xv_next registers);
-//   * the TMA ring is two stages deep and runs two tiles ahead; the fetch side needs no
-//     descriptor (chunk start / length are closed-form in (chunk, nnz, T), spmv.cpp:584-627), so it
-//     crosses chunk boundaries: the first tiles of the warp's next chunk are already in flight
-//     while the current chunk's tail is walked and its epilogue runs;
-//   * record batches are prefetched one batch (32 records) ahead, so the delivery loop does not
-//     wait on a dependent global load per batch.
-// Per tile g (stage s = g & 1):
-//   1. wait full[s^1]; read cols of tile g+1 from the stage; issue its gathers -> xv_next
-//   2. read vals of tile g (its barrier was waited for one iteration earlier)
-//   3. fence.proxy.async + syncwarp; lane 0 re-arms stage s with tile g+2
-//   4. deliver records, walk, carry chain, emits of tile g (chunk prologue / epilogue around it)
-//   5. xv <- xv_next
-// ---------------------------------------------------------------------------------------
-template <int TB>
-struct PipeGeo {
-    static constexpr int TILE = 4 * TB * CVR_W;
-    static constexpr int QUARTER = TB * CVR_W;
-    static constexpr int FLAG_WORDS = (TB + 3) / 4;
-    static constexpr int STAGE_BYTES = TILE * 12;        // vals then cols
-    static constexpr int WARP_SMEM = 2 * STAGE_BYTES;    // two stages per warp
-    static constexpr int DYN_SMEM = WARPS * WARP_SMEM;
-};
-
-template <int TB, int NB, bool kPublish>
-__global__ void __launch_bounds__(WARPS * 32, NB)
-cvr_spmv_pipe_kernel(const CvrChunk* __restrict__ chunks, int32_t T, int64_t nnz,
-                     const double* __restrict__ vals, const int32_t* __restrict__ cols,
-                     const int32_t* __restrict__ record, const double* __restrict__ x,
-                     double* __restrict__ y, const __grid_constant__ CvrPublish pub)
-{
-    using G = PipeGeo<TB>;
-    constexpr int TILE = G::TILE, QUARTER = G::QUARTER, FLAG_WORDS = G::FLAG_WORDS;
-    __shared__ uint32_t s_flags[WARPS][FLAG_WORDS][32]; // one flag byte per (thread, step)
-    __shared__ int32_t s_wb[WARPS][TB][32];             // write-back target per (step, thread)
-    __shared__ __align__(8) unsigned long long s_bar[WARPS][2];
-    extern __shared__ __align__(128) unsigned char s_stream[]; // WARPS x 2 stages
-
-    const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int q = t >> 3, l = t & 7;
-    const int32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    // iterated multi-GPU SpMV: the publish epilogue behind us is a programmatic dependent; let its
-    // blocks become resident as ours retire (it waits for this grid to complete before it reads y)
-    if (kPublish) asm volatile("griddepcontrol.launch_dependents;");
-    if (warp0 >= T) return; // no chunk for this warp (never with the launcher's grid)
-
-    const uint32_t ring = smem_u32(s_stream + w * G::WARP_SMEM);
-    const uint32_t bar0 = smem_u32(&s_bar[w][0]);
-    uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    if (t == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8u, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-#pragma unroll
-    for (int k = 0; k < FLAG_WORDS; k++) s_flags[w][k][t] = 0u;
-    __syncwarp();
-
-    // ---- fetch side: the warp's tile sequence (chunks warp0, warp0 + n_warps, ...; every tile of each)
-    // in closed form -- nnz-balanced slices in multiples of 16 (spmv.cpp:584-586, :615-627)
-    const int64_t per = (nnz / T / 16) * 16;
-    const int64_t brk = (nnz - per * T) / 16;
-    int32_t f_chunk = warp0, f_tile = 0, f_ntiles = 0, f_len = 0;
-    int64_t f_start = 0;
-    auto fetch_enter = [&](int32_t c) {
-        f_chunk = c;
-        f_tile = 0;
-        if (c < T) {
-            f_start = c < brk ? c * (per + 16) : c * per + brk * 16;
-            f_len = (int32_t)(c == T - 1 ? nnz - f_start : (c < brk ? per + 16 : per));
-            f_ntiles = (f_len + TILE - 1) / TILE;
-        }
-    };
-    // start the bulk copies of the next tile of the sequence into stage `sidx`; returns its element
-    // count (0: the sequence is exhausted)
-    auto fetch_issue = [&](uint32_t sidx) -> int32_t {
-        if (f_chunk >= T) return 0;
-        const int32_t ts = f_tile * TILE;
-        const int32_t n_el = min(TILE, f_len - ts); // multiple of 16
-        if (t == 0) {
-            const uint32_t bar = bar0 + 8u * sidx;
-            const uint32_t stage = ring + sidx * G::STAGE_BYTES;
-            mbar_expect_tx(bar, (uint32_t)n_el * 12u);
-            bulk_g2s(stage, vals + f_start + ts, (uint32_t)n_el * 8u, bar, policy);
-            bulk_g2s(stage + TILE * 8, cols + f_start + ts, (uint32_t)n_el * 4u, bar, policy);
-        }
-        if (++f_tile == f_ntiles) fetch_enter(f_chunk + n_warps);
-        return n_el;
-    };
-    fetch_enter(warp0);
-    int32_t nel0 = fetch_issue(0); // tile being walked
-    int32_t nel1 = fetch_issue(1); // tile whose gathers are in flight
-    int32_t nel2 = 0;              // tile just issued to the ring
-
-    // cols of a tile -> gathers of x (columns of elements past the chunk end read the phantom x[0])
-    auto gather_tile = [&](uint32_t sidx, int32_t n_el, double (&out)[TB]) {
-        const uint32_t* sc =
-            reinterpret_cast<const uint32_t*>(s_stream + w * G::WARP_SMEM + sidx * G::STAGE_BYTES + TILE * 8) +
-            q * QUARTER + l;
-        uint32_t ci[TB];
-        if (n_el == TILE) {
-#pragma unroll
-            for (int b = 0; b < TB; b++) ci[b] = sc[b * CVR_W];
-        } else {
-#pragma unroll
-            for (int b = 0; b < TB; b++) ci[b] = (q * QUARTER + l + b * CVR_W < n_el) ? sc[b * CVR_W] : 0u;
-        }
-#pragma unroll
-        for (int b = 0; b < TB; b++) out[b] = __ldg(x + ci[b]);
-    };
-
-    // ---- walk side: per-chunk state
-    int32_t chunk = warp0, w_tile = 0, w_ntiles = 1;
-    const CvrChunk* cp = chunks + chunk;
-    int32_t split0 = 0, n_rec = 0, chunk_last_row = 0;
-    const int2* rec = nullptr;
-    int32_t rb = 0;
-    int2 held = make_int2(-1, 0), nxt = make_int2(-1, 0);
-    double lane_carry = 0.0, carry_slot = 0.0;
-    TileCtx cx;
-    cx.y = y;
-    cx.pub = &pub;
-    cx.l = l;
-    cx.tail = cp->tail;
-    cx.scatter = false;
-    cx.split1 = 0;
-    cx.first_row = 0;
-
-    // When launched as a programmatic dependent (of the clearing kernel, or of the previous iteration's
-    // publish epilogue) everything above overlapped the predecessor's tail; x may only be read and y
-    // written once that grid has completed.  No-op for an ordinary launch.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-
-    double xv[TB], xv_next[TB];
-    mbar_wait(bar0, 0u);
-    gather_tile(0u, nel0, xv);
-
-    for (uint32_t g = 0;; g++) {
-        const uint32_t sidx = g & 1u;
-        // ---- 0. chunk prologue: descriptor and the first two record batches (their latency overlaps
-        // the barrier wait and the gathers below)
-        if (w_tile == 0) {
-            cp = chunks + chunk;
-            const int32_t len = cp->len;
-            split0 = cp->split0;
-            n_rec = cp->n_rec;
-            chunk_last_row = cp->last_row;
-            cx.tail = cp->tail;
-            cx.split1 = cp->split1;
-            cx.first_row = cp->first_row;
-            // A chunk in a very sparse region can span 10^5 (mostly empty) rows: pushing that range from
-            // one warp would serialise; such chunks publish their few finished rows one by one instead
-            cx.scatter = kPublish && ((pub.mode & 1) || chunk_last_row - cx.first_row >= PUSH_MAX_ROWS);
-            w_ntiles = (len + TILE - 1) / TILE;
-            rec = reinterpret_cast<const int2*>(record + cvr_record_offset(chunk, cx.first_row));
-            rb = 0;
-            held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
-            nxt = (32 + t < n_rec) ? rec[32 + t] : make_int2(-1, 0);
-            lane_carry = 0.0;
-            carry_slot = 0.0;
-        }
-        // ---- 1. operands: cols of tile g+1 (its gathers go out below) and vals of tile g, both from the ring
-        const int32_t ts = w_tile * TILE;
-        const int32_t p0 = ts + q * QUARTER + l; // my element of step TB*q of the tile; next step: +8
-        uint32_t ci[TB];
-        if (nel1 > 0) {
-            mbar_wait(bar0 + 8u * (sidx ^ 1u), ((g + 1u) >> 1) & 1u);
-            const uint32_t* sc = reinterpret_cast<const uint32_t*>(s_stream + w * G::WARP_SMEM +
-                                                                   (sidx ^ 1u) * G::STAGE_BYTES + TILE * 8) +
-                                 q * QUARTER + l;
-            if (nel1 == TILE) {
-#pragma unroll
-                for (int b = 0; b < TB; b++) ci[b] = sc[b * CVR_W];
-            } else {
-#pragma unroll
-                for (int b = 0; b < TB; b++) ci[b] = (q * QUARTER + l + b * CVR_W < nel1) ? sc[b * CVR_W] : 0u;
-            }
-        }
-        double a[TB];
-        {
-            const double* sv =
-                reinterpret_cast<const double*>(s_stream + w * G::WARP_SMEM + sidx * G::STAGE_BYTES) + q * QUARTER + l;
-            if (nel0 == TILE) {
-#pragma unroll
-                for (int b = 0; b < TB; b++) a[b] = sv[b * CVR_W];
-            } else {
-#pragma unroll
-                for (int b = 0; b < TB; b++) a[b] = (q * QUARTER + l + b * CVR_W < nel0) ? sv[b * CVR_W] : 0.0;
-            }
-        }
-        // ---- 2. stage `sidx` is free (cols read one iteration ago, vals just now): refill it with tile
-        // g+2.  The refill is an async-proxy write to memory these generic-proxy loads just read: fence in
-        // every reader, converge, then re-arm.  The fence (MEMBAR + FENCE.VIEW.ASYNC) waits for every
-        // memory operation of the thread that is still in flight, so it has to sit BEFORE the gathers go
-        // out -- behind them it would wait for them and serialise the pipeline (ncu: 8 % of the stall
-        // samples of the first version, profiles/r02_prof_pipe9x4_v1_rmat24_source_top.txt).
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        nel2 = fetch_issue(sidx);
-        // ---- 3. gathers of tile g+1: in flight while tile g is walked
-        if (nel1 > 0) {
-#pragma unroll
-            for (int b = 0; b < TB; b++) xv_next[b] = __ldg(x + ci[b]);
-        }
-
-        // ---- 4a. deliver the records of this tile to their owner threads
-        for (;;) {
-            const uint32_t rel = (uint32_t)(held.x - ts);
-            if (rel < (uint32_t)TILE) {
-                const uint32_t step = rel >> 3, wq = step / TB, b = step - wq * TB;
-                const uint32_t owner = wq * CVR_W + (rel & 7u);
-                reinterpret_cast<unsigned char*>(&s_flags[w][b >> 2][owner])[b & 3u] = 1;
-                s_wb[w][b][owner] = held.y;
-            }
-            // records are sorted by position: the batch reaches past the tile (or the list ended, pos = -1)
-            // as soon as ANY lane holds a position beyond it -- a vote, not a shuffle round trip through
-            // the load/store queue the gathers occupy
-            if (__any_sync(FULL, (uint32_t)held.x >= (uint32_t)(ts + TILE))) break;
-            rb += 32;
-            held = nxt;
-            nxt = (rb + 32 + t < n_rec) ? rec[rb + 32 + t] : make_int2(-1, 0);
-        }
-        if (t == 0 && split0 != 0) {
-            const uint32_t rel = (uint32_t)(split0 - ts);
-            if (rel < (uint32_t)TILE) {
-                const uint32_t step = rel >> 3, wq = step / TB, b = step - wq * TB;
-                const uint32_t owner = wq * CVR_W + (rel & 7u);
-                reinterpret_cast<unsigned char*>(&s_flags[w][b >> 2][owner])[b & 3u] = 1;
-                s_wb[w][b][owner] = WB_SPLIT0;
-            }
-        }
-        __syncwarp();
-        uint32_t mask = 0; // bit b: my SIMD lane switches rows before step b of my share
-#pragma unroll
-        for (int k = 0; k < FLAG_WORDS; k++) {
-            const uint32_t fw = s_flags[w][k][t];
-            if (fw) s_flags[w][k][t] = 0u;
-            mask |= bytes_to_bits(fw) << (4 * k);
-        }
-
-        // ---- 4b. walk my TB steps with two predicated FMA chains: `head` collects the steps before my
-        // first flag (everything if I have none), `tail` the steps from my last flag on.
-        const int b_first = mask ? __ffs(mask) - 1 : TB;
-        const int b_last = mask ? 31 - __clz(mask) : TB;
-        const uint32_t below = (1u << b_first) - 1u;        // steps before the first flag
-        const uint32_t after = ~((1u << b_last) - 1u);      // steps from the last flag on
-        double head = 0.0, tailsum = 0.0;
-        const uint32_t after_m = mask ? after : 0u;
-#pragma unroll
-        for (int b = 0; b < TB; b++) {
-            fma_if(head, a[b], xv[b], below & (1u << b));
-            fma_if(tailsum, a[b], xv[b], after_m & (1u << b));
-        }
-        // segments strictly between two flags of the same thread (short rows): emit in place
-        if (b_last > b_first) {
-            double acc = 0.0;
-#pragma unroll
-            for (int b = 0; b < TB; b++) {
-                if (b > b_first && ((mask >> b) & 1u)) {
-                    emit<kPublish>(cx, acc, p0 + b * CVR_W, s_wb[w][b][t], carry_slot);
-                    acc = 0.0;
-                }
-                if (b >= b_first && b < b_last) acc = fma(a[b], xv[b], acc);
-            }
-        }
-
-        // ---- 4c. carry chain over the four walkers of my SIMD lane.  Walker r hands on
-        // out_r = has_r ? tail_r : cin_r + head_r, cin_r = out_(r-1), cin_0 = the lane's carry from the
-        // previous tile.  With v_r = has_r ? tail_r : head_r that is out_r = v_r + (has_r ? 0 : cin_r): every
-        // thread fetches the three other v of its SIMD lane with INDEPENDENT shuffles (they pipeline through
-        // the load/store queue; the dependent shuffle chain of round 1 cost three queue round trips) and the
-        // has-flags with one vote, then folds the chain locally.
-        const bool has = mask != 0u;
-        const unsigned has_all = __ballot_sync(FULL, has);
-        const double v_mine = has ? tailsum : head;
-        double vq[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) vq[r] = __shfl_sync(FULL, v_mine, r * CVR_W + l);
-        double run = lane_carry, cin = lane_carry; // run = out_(r-1) while folding
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            if (r == q) cin = run;
-            run = ((has_all >> (r * CVR_W + l)) & 1u) ? vq[r] : run + vq[r];
-        }
-        lane_carry = run;
-        if (has) emit<kPublish>(cx, head + cin, p0 + b_first * CVR_W, s_wb[w][b_first][t], carry_slot);
-        __syncwarp(); // slots are reused by the next tile's delivery
-
-        // ---- 4d. chunk epilogue: lane remainders through the eight pos=-1 records (spmv.cpp:1633-1649)
-        if (++w_tile == w_ntiles) {
-            double carry = carry_slot + __shfl_xor_sync(FULL, carry_slot, 8);
-            carry += __shfl_xor_sync(FULL, carry, 16);
-            const int32_t term_wb = (t < CVR_W) ? rec[n_rec + t].y : 0;
-#pragma unroll
-            for (int k = 0; k < CVR_W; k++) {
-                const double r = __shfl_sync(FULL, lane_carry, k);
-                const int32_t wbk = __shfl_sync(FULL, term_wb, k);
-                if (t == wbk) carry += r;
-            }
-            if (t < CVR_W) {
-                const int32_t row = cp->tail[t];
-                if (row != 0) atomicAdd(&y[row], carry); // row 0 = phantom row of unused lanes (carry 0.0)
-            }
-            if (kPublish && !cx.scatter && (!pub.chunk_any || pub.chunk_any[chunk]))
-                publish_chunk_rows(cx, cx.first_row, chunk_last_row, t);
-            chunk += n_warps;
-            w_tile = 0;
-        }
-
-        // ---- 5. rotate the pipeline
-        if (nel1 == 0) break;
-#pragma unroll
-        for (int b = 0; b < TB; b++) xv[b] = xv_next[b];
-        nel0 = nel1;
-        nel1 = nel2;
-    }
-}
-
-constexpr int TB_TILE = 9; // round-1 kernel: tile = 288 elements
-static_assert(TB_TILE % 2 == 1, "the TMA tile needs an odd number of steps per walker (bank layout)");
 
 // ---- small helper kernels around the sweep
 // y is cleared only where it is accumulated (boundary rows) or never written (empty rows, row 0):
@@ -852,41 +520,31 @@ __global__ void cvr_peer_barrier_kernel(const __grid_constant__ CvrBarrier b)
     peer_flag_barrier(b, threadIdx.x);
 }
 
-// ---- sweep variants.  `pipeTxB` = cvr_spmv_pipe_kernel<T, B>: T steps per walker (tile = 32 T
-// elements), B resident blocks (4 warps each) per SM requested through __launch_bounds__.
+// ---- sweep geometries: cvr_spmv_tile_kernel<TB, NB>, TB steps per walker (tile = 32 TB elements), NB
+// resident blocks (4 warps each) per SM requested through __launch_bounds__.  Measured on B200
+// (profiles/r02_kernel_ab_tile_geometries.jsonl, kernel us): FEM 70.3 / 65.3 / 62.9, R-MAT-24 1358 / 1387 /
+// 1369, web 38.3 / 40.3 / 41.3, road 342.8 / 354.6 / 370.9 for 7x7 / 9x6 / 11x5 -- short rows want more
+// warps, long regular rows want the larger tile (fewer per-tile flag/carry operations per element).
 struct Variant {
     const char* name;
-    bool pipe;
     int tb, nb;
 };
 constexpr Variant VARIANTS[] = {
-    {"tile", false, TB_TILE, CVR_TMA_BLOCKS},
-    {"pipe9x4", true, 9, 4},
-    {"pipe7x4", true, 7, 4},
-    {"pipe7x5", true, 7, 5},
-    {"pipe5x5", true, 5, 5},
-    {"pipe5x6", true, 5, 6},
-    {"pipe9x3", true, 9, 3},
-    {"tile7x7", true, 7, 7},
-    {"tile7x8", true, 7, 8},
-    {"tile11x5", true, 11, 5},
-    {"tile13x4", true, 13, 4},
-    {"tile5x8", true, 5, 8},
+    {"tile7x7", 7, 7},
+    {"tile11x5", 11, 5},
+    {"tile9x6", 9, 6},
 };
 constexpr int N_VARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
-#ifndef CVR_DEFAULT_VARIANT
-#define CVR_DEFAULT_VARIANT 1
-#endif
 
-int selected_variant()
+int forced_variant()
 {
-    // CVR_SPMV_KERNEL = tile | pipe (= the default) | pipe<T>x<B>; read per call so that
-    // tools/kernel_ab.py and the parity suite can switch it at run time
+    // CVR_SPMV_KERNEL = tile7x7 | tile11x5 | tile9x6 overrides the per-matrix choice; read per call so
+    // that tools/kernel_ab.py and the parity suite can switch it at run time
     const char* e = getenv("CVR_SPMV_KERNEL");
-    if (!e || !*e || strcmp(e, "pipe") == 0) return CVR_DEFAULT_VARIANT;
+    if (!e || !*e) return -1;
     for (int v = 0; v < N_VARIANTS; v++)
         if (strcmp(e, VARIANTS[v].name) == 0) return v;
-    return CVR_DEFAULT_VARIANT;
+    return -1;
 }
 
 template <typename K, typename... Args>
@@ -906,7 +564,7 @@ cudaError_t launch_ex(K kernel, int blocks, int threads, int smem, cudaStream_t 
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-// experimental geometries of the round-1 kernel (plain flavour only): "tile<T>x<B>"
+// one entry per geometry: occupancy query and launch, plain and publishing flavour
 template <int TB, int NB>
 struct TileOps {
     static int resident_blocks()
@@ -918,11 +576,12 @@ struct TileOps {
         return blocks;
     }
     static cudaError_t launch(bool publish, int blocks, cudaStream_t stream, bool programmatic,
-                              const CvrChunk* chunks, int32_t T, int64_t, const double* vals,
-                              const int32_t* cols, const int32_t* record, const double* x, double* y,
-                              const CvrPublish& pub)
+                              const CvrChunk* chunks, int32_t T, const double* vals, const int32_t* cols,
+                              const int32_t* record, const double* x, double* y, const CvrPublish& pub)
     {
-        if (publish) return cudaErrorNotSupported;
+        if (publish)
+            return launch_ex(cvr_spmv_tile_kernel<TB, NB, true>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
+                             programmatic, chunks, T, vals, cols, record, x, y, pub);
         return launch_ex(cvr_spmv_tile_kernel<TB, NB, false>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
                          programmatic, chunks, T, vals, cols, record, x, y, pub);
     }
@@ -930,52 +589,15 @@ struct TileOps {
     {
         cudaFuncAttributes a;
         cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, false>);
+        cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, true>);
     }
 };
 
-// one entry per variant: occupancy query and launch, plain and publishing flavour
-template <int TB, int NB>
-struct PipeOps {
-    static int resident_blocks()
-    {
-        int blocks = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_pipe_kernel<TB, NB, false>, WARPS * 32,
-                                                          PipeGeo<TB>::DYN_SMEM) != cudaSuccess)
-            return 0;
-        return blocks;
-    }
-    static cudaError_t launch(bool publish, int blocks, cudaStream_t stream, bool programmatic,
-                              const CvrChunk* chunks, int32_t T, int64_t nnz, const double* vals,
-                              const int32_t* cols, const int32_t* record, const double* x, double* y,
-                              const CvrPublish& pub)
-    {
-        if (publish)
-            return launch_ex(cvr_spmv_pipe_kernel<TB, NB, true>, blocks, WARPS * 32, PipeGeo<TB>::DYN_SMEM, stream,
-                             programmatic, chunks, T, nnz, vals, cols, record, x, y, pub);
-        return launch_ex(cvr_spmv_pipe_kernel<TB, NB, false>, blocks, WARPS * 32, PipeGeo<TB>::DYN_SMEM, stream,
-                         programmatic, chunks, T, nnz, vals, cols, record, x, y, pub);
-    }
-    static void preload()
-    {
-        cudaFuncAttributes a;
-        cudaFuncGetAttributes(&a, cvr_spmv_pipe_kernel<TB, NB, false>);
-    }
-};
-
-#define CVR_FOR_PIPE_VARIANT(v, expr)                   \
-    switch (v) {                                        \
-    case 1: { using P = PipeOps<9, 4>; expr; } break;   \
-    case 2: { using P = PipeOps<7, 4>; expr; } break;   \
-    case 3: { using P = PipeOps<7, 5>; expr; } break;   \
-    case 4: { using P = PipeOps<5, 5>; expr; } break;   \
-    case 5: { using P = PipeOps<5, 6>; expr; } break;   \
-    case 6: { using P = PipeOps<9, 3>; expr; } break;   \
-    case 7: { using P = TileOps<7, 7>; expr; } break;   \
-    case 8: { using P = TileOps<7, 8>; expr; } break;   \
-    case 9: { using P = TileOps<11, 5>; expr; } break;  \
-    case 10: { using P = TileOps<13, 4>; expr; } break; \
-    case 11: { using P = TileOps<5, 8>; expr; } break;  \
-    default: break;                                     \
+#define CVR_FOR_VARIANT(v, expr)                         \
+    switch (v) {                                         \
+    case 0: { using P = TileOps<7, 7>; expr; } break;    \
+    case 1: { using P = TileOps<11, 5>; expr; } break;   \
+    default: { using P = TileOps<9, 6>; expr; } break;   \
     }
 
 // resident blocks per SM of a variant on the current device (cached per device and variant)
@@ -987,13 +609,7 @@ int variant_resident_blocks(int v)
     int* slot = (dev >= 0 && dev < 64) ? &cache[dev][v] : nullptr;
     if (slot && *slot > 0) return *slot;
     int blocks = 0;
-    if (!VARIANTS[v].pipe) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<TB_TILE, CVR_TMA_BLOCKS, false>, WARPS * 32,
-                                                          Geo<TB_TILE>::DYN_SMEM) != cudaSuccess)
-            blocks = 0;
-    } else {
-        CVR_FOR_PIPE_VARIANT(v, blocks = P::resident_blocks())
-    }
+    CVR_FOR_VARIANT(v, blocks = P::resident_blocks())
     if (blocks <= 0) blocks = 4;
     if (slot) *slot = blocks;
     return blocks;
@@ -1018,36 +634,37 @@ bool pdl_enabled()
 
 } // namespace
 
-void cvr_preload_spmv_kernels()
+// Geometry for a matrix with `nnz` stored elements in `n_rows` rows: the larger tile pays off when rows
+// are long and regular (few row switches per tile: FEM), more resident warps when they are short or
+// skewed (web, road, R-MAT).  CVR_SPMV_KERNEL overrides.
+int cvr_pick_sweep_variant(int64_t nnz, int64_t n_rows)
 {
-    cudaFuncAttributes a;
-    const int v = selected_variant();
-    if (!VARIANTS[v].pipe) cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB_TILE, CVR_TMA_BLOCKS, false>);
-    else {
-        CVR_FOR_PIPE_VARIANT(v, P::preload())
-    }
-    cudaFuncGetAttributes(&a, cvr_clear_rows_kernel);
+    const int f = forced_variant();
+    if (f >= 0) return f;
+    return (n_rows > 0 && nnz / n_rows >= 20) ? 1 : 0;
 }
 
-// resident warps per SM of the selected kernel (used to size the automatic chunk count)
-int cvr_spmv_resident_warps_per_sm()
+// resident warps per SM of a variant (sizes the automatic chunk count)
+int cvr_spmv_resident_warps_per_sm(int variant)
 {
-    return variant_resident_blocks(selected_variant()) * WARPS;
+    return variant_resident_blocks(variant) * WARPS;
 }
 
-const char* cvr_spmv_kernel_name()
+const char* cvr_spmv_kernel_name(int variant)
 {
-    return VARIANTS[selected_variant()].name;
+    const int f = forced_variant();
+    return VARIANTS[f >= 0 ? f : variant].name;
 }
 
-int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, int64_t nnz, const double* vals,
+int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const double* vals,
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
                     int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
                     cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end,
                     const CvrBarrier* barrier, unsigned int* done_counter, bool y_is_clear)
 {
     int launched = 0;
-    const int v = selected_variant();
+    const int f = forced_variant();
+    const int v = f >= 0 ? f : variant;
     const int sms = device_sm_count();
     const int32_t n_clear = rows.n_boundary + rows.n_empty;
     bool after_clear_kernel = false;
@@ -1072,20 +689,12 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, int64_t nnz, const
     const bool pub = publish && publish->n_dst > 0;
     // the kernel in front of us on the stream is the clearing kernel or (iterated SpMV, from the second
     // iteration on) the previous iteration's epilogue: launch as its programmatic dependent
-    const bool programmatic = pdl_enabled() && (after_clear_kernel || (pub && y_is_clear)) && !ev_begin;
+    const bool pdl = pdl_enabled() && !(pub && (publish->mode & 8)); // mode bit 3: two shards share this device
+    const bool programmatic = pdl && (after_clear_kernel || (pub && y_is_clear)) && !ev_begin;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
     cudaError_t e = cudaSuccess;
-    if (!VARIANTS[v].pipe) {
-        if (pub)
-            e = launch_ex(cvr_spmv_tile_kernel<TB_TILE, CVR_TMA_BLOCKS, true>, pblocks, threads, Geo<TB_TILE>::DYN_SMEM, stream,
-                          programmatic, chunks, n_chunks, vals, cols, record, x, y, *publish);
-        else
-            e = launch_ex(cvr_spmv_tile_kernel<TB_TILE, CVR_TMA_BLOCKS, false>, pblocks, threads, Geo<TB_TILE>::DYN_SMEM, stream,
-                          programmatic, chunks, n_chunks, vals, cols, record, x, y, none);
-    } else {
-        CVR_FOR_PIPE_VARIANT(v, e = P::launch(pub, pblocks, stream, programmatic, chunks, n_chunks, nnz, vals, cols,
-                                              record, x, y, pub ? *publish : none))
-    }
+    CVR_FOR_VARIANT(v, e = P::launch(pub, pblocks, stream, programmatic, chunks, n_chunks, vals, cols, record, x, y,
+                                     pub ? *publish : none))
     if (e != cudaSuccess) return -1;
     launched++;
     if (ev_end) cudaEventRecord(ev_end, stream);
@@ -1094,7 +703,7 @@ int cvr_launch_spmv(const CvrChunk* chunks, int32_t n_chunks, int64_t nnz, const
         const int cb = (n_clear + 255) / 256;
         const int cap = sms * 4;
         e = launch_ex(cvr_publish_epilogue_kernel, cb < cap ? (cb < 1 ? 1 : cb) : cap, 256, 0, stream,
-                      pdl_enabled() && !ev_end, y, (const int32_t*)rows.boundary, rows.n_boundary,
+                      pdl && !ev_end, y, (const int32_t*)rows.boundary, rows.n_boundary,
                       (const int32_t*)rows.empty, rows.n_empty, *publish, *barrier, done_counter);
         if (e != cudaSuccess) return -1;
         launched++;
@@ -1144,3 +753,20 @@ int cvr_launch_peer_barrier(const CvrBarrier& b, cudaStream_t stream)
     cvr_peer_barrier_kernel<<<1, 32, 0, stream>>>(b);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
+
+void cvr_preload_spmv_kernels()
+{
+    cudaFuncAttributes a;
+    for (int v = 0; v < N_VARIANTS; v++) {
+        CVR_FOR_VARIANT(v, P::preload())
+    }
+    cudaFuncGetAttributes(&a, cvr_clear_rows_kernel);
+    // The multi-GPU kernels wait for each other on the device (flag barrier).  CUDA loads a kernel lazily at
+    // its first launch and that load can synchronise with running work: a first launch issued while a peer's
+    // epilogue is already spinning at the barrier would never get through.  Load everything up front.
+    cudaFuncGetAttributes(&a, cvr_publish_epilogue_kernel);
+    cudaFuncGetAttributes(&a, cvr_peer_barrier_kernel);
+    cudaFuncGetAttributes(&a, cvr_column_footprint_kernel);
+    cudaFuncGetAttributes(&a, cvr_chunk_needs_kernel);
+}
+

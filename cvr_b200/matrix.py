@@ -58,13 +58,7 @@ class CvrMatrix:
         lib = _lib.load()
         self._lib = lib
         self._h = C.c_void_p()
-        desc = _lib.CvrCsr()
-        desc.n_rows, desc.n_cols, desc.nnz = csr.n_rows, csr.n_cols, csr.nnz
-        desc.val, desc.col = _ptr(csr.val), _ptr(csr.col)
-        rd = csr.row_delim
-        wide = (rd.dtype == np.int64) if isinstance(rd, np.ndarray) else ("int64" in str(rd.dtype))
-        desc.row_delim32 = 0 if wide else _ptr(rd)
-        desc.row_delim64 = _ptr(rd) if wide else 0
+        desc = _csr_desc(csr)
         if isinstance(csr, DeviceCsr):
             if csr.device.type != "cuda":
                 raise ValueError("DeviceCsr must live on a CUDA device (no CPU path)")
@@ -129,8 +123,8 @@ class CvrMatrix:
 
     @property
     def kernel_name(self) -> str:
-        """The sweep kernel variant CVR_SPMV_KERNEL selects right now ("pipe9x4", "tile", ...)."""
-        return self._lib.cvr_kernel_variant().decode()
+        """The sweep geometry picked for this matrix ("tile7x7", "tile11x5"; CVR_SPMV_KERNEL overrides)."""
+        return self._lib.cvr_kernel_variant(self._h).decode()
 
     def column_footprint(self, used_dev, stream: int = 0) -> None:
         """used_dev[c] = 1 (uint8, n_cols+1 entries, pre-zeroed) for every column id this matrix touches."""
@@ -202,6 +196,73 @@ class CvrMatrix:
         arr = _lib.CvrArrays(*(out[k].ctypes.data for k in ("vals", "cols", "record", "nnz_rows", "final_2", "split")))
         _lib.check(self._lib.cvr_export(self._h, C.byref(arr)))
         return out
+
+
+class ShardedCvr:
+    """The matrix row-sharded over several GPUs by ONE process (cvr_create_sharded): thin wrapper over the
+    C++ multi-device host of libcvr_b200.  `devices` may repeat a device (several shards on one GPU)."""
+
+    def __init__(self, csr: CsrMatrix, devices, n_chunks: int = 0, exchange: str = "peer", dense: bool = False):
+        lib = _lib.load()
+        self._lib = lib
+        self._h = C.c_void_p()
+        desc = _csr_desc(csr)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        flags = (_lib.SHARD_NCCL if exchange == "nccl" else _lib.SHARD_PEER) | (_lib.SHARD_DENSE if dense else 0)
+        _lib.check(lib.cvr_create_sharded(C.byref(desc), int(n_chunks), devs, len(devices), flags, C.byref(self._h)))
+        self.n_rows, self.n_cols = csr.n_rows, csr.n_cols
+
+    @property
+    def info(self) -> dict:
+        i = _lib.CvrShardedInfo()
+        _lib.check(self._lib.cvr_sharded_get_info(self._h, C.byref(i)))
+        n = i.n_parts
+        out = {name: getattr(i, name) for name, _ in _lib.CvrShardedInfo._fields_}
+        for k in ("device", "row_begin", "row_end", "part_nnz", "part_chunks", "peer_bytes_per_iter"):
+            out[k] = list(out[k])[:n]
+        return out
+
+    def spmv(self, x, iters: int = 1, feed_y_to_x: bool = False):
+        """(y[n_rows+1], seconds per iteration): `iters` SpMVs with the same x, or `iters` iterations of
+        x <- A x with one exchange each when feed_y_to_x."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.shape[0] != self.n_cols + 1:
+            raise ValueError(f"x must have n_cols+1 = {self.n_cols + 1} entries")
+        y = np.empty(self.n_rows + 1, dtype=np.float64)
+        secs = C.c_double()
+        _lib.check(self._lib.cvr_sharded_spmv(self._h, x.ctypes.data, y.ctypes.data, int(iters), int(feed_y_to_x),
+                                              C.byref(secs)))
+        return y, secs.value
+
+    def part_export(self, part: int) -> dict:
+        """CVR structure arrays of one shard in the reference layout (the bit-exact gate per shard)."""
+        h = C.c_void_p()
+        _lib.check(self._lib.cvr_sharded_part(self._h, int(part), C.byref(h)))
+        view = CvrMatrix.__new__(CvrMatrix)
+        view._lib, view._h = self._lib, h
+        i = view.info
+        view.n_rows, view.n_cols, view.nnz, view.nnz_true = i["n_rows"], i["n_cols"], i["nnz"], i["nnz"]
+        try:
+            return view.export()
+        finally:
+            view._h = C.c_void_p()  # owned by the sharded handle
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.cvr_sharded_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def _csr_desc(csr):

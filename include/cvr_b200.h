@@ -158,6 +158,7 @@ typedef struct cvr_publish {
     int32_t self;        /* index of this GPU's own buffer in dst[] (required with mode bit 2) */
     int32_t mode;        /* bit 0: per-row stores instead of the coalesced per-chunk push (A/B);
                             bit 1: skip the 0.0 for never-written rows (set from the 3rd iteration on);
+                            bit 3: no programmatic dependent launches (set when one device carries two shards);
                             bit 2: y_dev IS this GPU's own slice of the next x (x_next + row_offset), so
                                    own rows need no copy; then leave this GPU's bit out of `needs`, and
                                    set clear_next = x_current + row_offset (the next iteration's y) */
@@ -197,6 +198,44 @@ int cvr_peer_free(int device, void* dev_ptr);
 int cvr_peer_barrier(int device, void* const* flag_arrays, int32_t rank, int32_t n_ranks, uint32_t epoch,
                      void* cuda_stream);
 
+/* ---- the same path on 1..8 GPUs from ONE process (the host the `spmv.cvr` CLI uses with CVR_DEVICES) ----
+ * cvr_create_sharded cuts the host CSR into n_devices contiguous row ranges of equal nnz (snapped to row
+ * starts, the bisection of spmv.cpp:631-650), uploads and converts each shard on its device (what
+ * pre_processing does per OpenMP thread slice, one level up) and prepares the exchange.  A device may be
+ * listed more than once (several shards on one GPU).
+ * cvr_sharded_spmv replaces spmv_compute_kernel (spmv.cpp:1016) with HOST vectors:
+ *   feed_y_to_x == 0: `iters` SpMVs with the same x (the reference's loop, :1024-1034); no communication;
+ *                     y_host[1..n_rows] = A x.
+ *   feed_y_to_x != 0: `iters` iterations of x <- A x (square A), one exchange per iteration -- fused into
+ *                     the sweep over NVLink peer memory (CVR_SHARD_PEER) or an NCCL all-gather after it
+ *                     (CVR_SHARD_NCCL); y_host[1..n_rows] = the last iterate.
+ * seconds_per_iter: host wall clock around the iteration loop (all devices synchronised on both sides). */
+typedef struct cvr_sharded cvr_sharded_t;
+#define CVR_SHARD_PEER 0  /* exchange fused into the sweep kernel over peer memory (default) */
+#define CVR_SHARD_NCCL 1  /* NCCL broadcasts after the sweep (libnccl.so.2 is loaded on first use) */
+#define CVR_SHARD_DENSE 2 /* CVR_SHARD_PEER: publish every row to every device, not only to its readers */
+typedef struct cvr_sharded_info {
+    int32_t n_parts;
+    int32_t exchange;                 /* 0 = peer, 1 = NCCL */
+    int64_t n_rows, n_cols, nnz;
+    int32_t device[8];
+    int64_t row_begin[8], row_end[8]; /* part g owns global rows [row_begin, row_end), 1-based */
+    int64_t part_nnz[8];              /* padded nnz of the shard */
+    int32_t part_chunks[8];
+    int64_t peer_bytes_per_iter[8];   /* bytes part g stores into other parts' x per iteration (sparse exchange) */
+    double create_seconds;            /* partition + upload + conversion + exchange set-up, host wall clock */
+    double convert_seconds;           /* sum of the per-device conversion times (CUDA events) */
+    int64_t kernel_launches;
+} cvr_sharded_info_t;
+int cvr_create_sharded(const cvr_csr_t* csr_host, int32_t n_chunks_per_device, const int* devices, int n_devices,
+                       int flags, cvr_sharded_t** out);
+int cvr_sharded_spmv(cvr_sharded_t* s, const double* x_host, double* y_host, int32_t iters, int32_t feed_y_to_x,
+                     double* seconds_per_iter);
+int cvr_sharded_get_info(cvr_sharded_t* s, cvr_sharded_info_t* info);
+/* the single-GPU handle of one part (owned by `s`), e.g. for cvr_export of a shard */
+int cvr_sharded_part(cvr_sharded_t* s, int part, cvr_handle_t** handle);
+void cvr_sharded_destroy(cvr_sharded_t* s);
+
 /* Replaces the reference's self-check (spmv.cpp:1843-1850 scalar CSR SpMV, :1916-1938 comparison) on
  * the device: y_dev against the CSR product of `csr_dev` (DEVICE pointers) and x_dev, row by row,
  * |y_r - sum_j a_rj x_j| <= rel_tol * sum_j |a_rj x_j| for rows 1..n_rows (row 0, the phantom, must be
@@ -221,8 +260,9 @@ int cvr_get_info(cvr_handle_t* h, cvr_info_t* info);
  * doubles), for callers that iterate on the device. */
 int cvr_device_vectors(cvr_handle_t* h, double** x_dev, double** y_dev);
 
-/* Name of the sweep kernel variant in use ("pipe9x4", "tile", ...; CVR_SPMV_KERNEL selects). */
-const char* cvr_kernel_variant(void);
+/* Name of the sweep geometry picked for this matrix ("tile7x7": short or skewed rows, "tile11x5": long
+ * regular rows; CVR_SPMV_KERNEL overrides). */
+const char* cvr_kernel_variant(cvr_handle_t* h);
 
 /* Device pointers of the converted matrix itself (read-only views, valid until cvr_destroy):
  * vals [nnz] f64, cols [nnz] i32 in CVR order, record [record_ints] i32.  For tools that run their

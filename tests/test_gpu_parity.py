@@ -27,6 +27,17 @@ def cvr(native_lib):
     return cvr_b200
 
 
+# every test of this module runs once per sweep geometry: the per-matrix choice (cvr_pick_sweep_variant)
+# and each geometry forced through CVR_SPMV_KERNEL (read per launch)
+@pytest.fixture(autouse=True, params=["auto", "tile7x7", "tile11x5", "tile9x6"])
+def sweep_geometry(request, monkeypatch):
+    if request.param == "auto":
+        monkeypatch.delenv("CVR_SPMV_KERNEL", raising=False)
+    else:
+        monkeypatch.setenv("CVR_SPMV_KERNEL", request.param)
+    return request.param
+
+
 def host_csr(cvr, c):
     return cvr.CsrMatrix(c.n_rows, c.n_cols, c.val, c.col, c.row_delim, c.nnz_file)
 
@@ -133,6 +144,27 @@ def test_auto_chunks_and_device_csr_entry(cvr):
                                                + 8 * (csr.n_cols + 1) + 8 * (csr.n_rows + 1))
 
 
+def test_iteration_loop_replayed_from_a_cuda_graph(cvr, monkeypatch):
+    """cvr_spmv with many iterations replays a captured graph of 20 iterations (the reference's loop,
+    spmv.cpp:1024-1034): same y as the plain loop, every iteration re-clears the accumulated rows, and the
+    launch count is what the plain loop would have issued."""
+    from cvr_b200 import gen
+    d = gen.powerlaw_web(20000, 110000, seed=52)
+    csr = to_oracle_csr(d)
+    x = np.random.default_rng(12).uniform(-1, 1, csr.n_cols + 1)
+    with cvr.CvrMatrix(d.to_host(), 300) as m:
+        l0 = m.info["kernel_launches"]
+        y_graph, secs = m.spmv(x, iters=45)  # 2 graph launches + 5 plain iterations
+        assert secs > 0 and m.info["kernel_launches"] - l0 == 90
+        assert_y_close(y_graph, csr, x, "graph loop")
+        monkeypatch.setenv("CVR_NO_GRAPH", "1")
+        y_plain, _ = m.spmv(x, iters=45)
+        assert_y_close(y_plain, csr, x, "plain loop")
+        monkeypatch.delenv("CVR_NO_GRAPH")
+        y_again, _ = m.spmv(2.0 * x, iters=21)  # the cached graph reads the handle's x buffer: new x, same graph
+        assert_y_close(y_again, csr, 2.0 * x, "graph loop, second x")
+
+
 def test_save_load_round_trip(cvr, tmp_path):
     """cvr_save / cvr_load: the reloaded matrix exports the same structure bit for bit and gives the
     same y (conversion skipped)."""
@@ -204,6 +236,67 @@ def test_full_size_properties_linearity_and_checksum(cvr):
         lin = (ys[2] - (2.0 * ys[0] - 3.0 * ys[1])).abs()
         assert bool((lin <= 1e-11 * (mag + 1.0)).all())
         assert abs(float(ys[0].sum() - y_ref.sum())) <= 1e-9 * float(mag.sum())
+
+
+def test_reference_last_delimiter_quirk_is_repaired(cvr):
+    """The reference reader leaves row_delim[k] = nnz-1 after the last non-empty row (spmv.cpp:522-526).
+    Such a CSR -- also with trailing EMPTY rows, where the reference reads out of bounds -- must convert to
+    exactly what the correct delimiters give, from host and from device memory, and must not hang."""
+    import torch
+    from test_oracle_property import build_csr
+    for lens in ([3, 0, 5, 2, 7, 4, 0, 0], [9, 1, 30, 2], [5, 5, 5, 0, 6, 2, 0, 0, 0, 0], [40, 3, 0, 17, 2]):
+        csr = build_csr(lens, seed=len(lens))
+        rd_quirk = csr.row_delim.copy()
+        rd_quirk[rd_quirk == csr.nnz] = csr.nnz - 1
+        assert rd_quirk[-1] == csr.nnz - 1
+        x = np.random.default_rng(11).uniform(-1, 1, csr.n_cols + 1)
+        for T in (1, max(1, csr.nnz // 32)):
+            want = oracle.convert(csr, T, "port", fill_missing_tail=True)
+            host = cvr.CsrMatrix(csr.n_rows, csr.n_cols, csr.val, csr.col, rd_quirk, csr.nnz_file)
+            with cvr.CvrMatrix(host, T) as m:
+                assert_structure_equal(m.export(), want, f"quirk host lens={lens} T={T}")
+                y, _ = m.spmv(x)
+                assert_y_close(y, csr, x, f"quirk host lens={lens} T={T}")
+            dev = cvr.DeviceCsr(csr.n_rows, csr.n_cols, torch.from_numpy(csr.val).cuda(),
+                                torch.from_numpy(csr.col).cuda(), torch.from_numpy(rd_quirk).cuda(), csr.nnz_file)
+            with cvr.CvrMatrix(dev, T) as m:
+                assert_structure_equal(m.export(), want, f"quirk device lens={lens} T={T}")
+    bad = csr.row_delim.copy()
+    bad[-1] = csr.nnz - 5
+    with pytest.raises(cvr.CvrError):
+        cvr.CvrMatrix(cvr.CsrMatrix(csr.n_rows, csr.n_cols, csr.val, csr.col, bad, csr.nnz_file), 1)
+    bad = csr.row_delim.copy()
+    bad[2] = bad[3] + 1  # decreasing
+    with pytest.raises(cvr.CvrError):
+        cvr.CvrMatrix(cvr.CsrMatrix(csr.n_rows, csr.n_cols, csr.val, csr.col, bad, csr.nnz_file), 1)
+
+
+def test_device_self_check_agrees_with_the_oracle_loop(cvr):
+    """cvr_verify_csr (the device restatement of the reference's verdict, spmv.cpp:1843-1850/:1916-1938) against
+    the oracle's scalar CSR loop: accepts the CVR result, rejects a planted error, reports its row."""
+    import torch
+    from cvr_b200 import gen
+    d = gen.powerlaw_web(30000, 160000, device="cuda", seed=51)
+    csr = to_oracle_csr(d)
+    x = np.random.default_rng(8).uniform(-1, 1, csr.n_cols + 1)
+    yc, mag = oracle.csr_spmv(csr, x)
+    xd = torch.from_numpy(x).cuda()
+    ok = cvr.verify_csr(d, xd, torch.from_numpy(yc).cuda())
+    assert ok["rows_failing"] == 0 and ok["first_bad_row"] == -1 and ok["max_rel"] <= 1e-13
+    with cvr.CvrMatrix(d, 0) as m:
+        yd = torch.empty(csr.n_rows + 1, dtype=torch.float64, device="cuda")
+        m.spmv_device(xd, yd)
+        torch.cuda.synchronize()
+        got = cvr.verify_csr(d, xd, yd)
+        assert got["rows_failing"] == 0 and got["max_rel"] <= 1e-12
+        assert_y_close(yd.cpu().numpy(), csr, x, "device y")
+        row = int(np.flatnonzero(mag > 0)[7])
+        yd[row] += 1e-9 * mag[row]
+        bad = cvr.verify_csr(d, xd, yd)
+        assert bad["rows_failing"] == 1 and bad["first_bad_row"] == row and bad["max_rel"] > 1e-10
+        yd[0] = 1.0  # the phantom row must stay 0
+        assert cvr.verify_csr(d, xd, yd)["rows_failing"] == 2
+        assert cvr.verify_csr(d, xd, yd, check_row0=False)["rows_failing"] == 1
 
 
 def test_cli_prints_the_reference_lines(cvr, tmp_path):
