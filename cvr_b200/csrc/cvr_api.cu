@@ -34,9 +34,14 @@ namespace {
                         __FILE__, __LINE__);                                                \
     } while (0)
 
-// bound of the peer-barrier spin: CVR_BARRIER_TIMEOUT_MS (default 3000) in SM clocks of `device`
+// bound of the peer-barrier spin: CVR_BARRIER_TIMEOUT_MS (default 3000) in SM clocks of `device`.
+// Computed once per device: cudaDevAttrClockRate is a driver query that takes about a millisecond, and
+// this is called on every iteration of the multi-GPU loop (the first N = 2 runs of round 2 spent 1-5 ms
+// per step here, profiles/r02_bench_n2_diagnostics.txt).
 long long barrier_timeout_cycles(int device)
 {
+    static long long cache[64] = {};
+    if (device >= 0 && device < 64 && cache[device] > 0) return cache[device];
     long long ms = 3000;
     if (const char* e = getenv("CVR_BARRIER_TIMEOUT_MS")) {
         const long long v = atoll(e);
@@ -44,7 +49,9 @@ long long barrier_timeout_cycles(int device)
     }
     int khz = 0;
     if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) != cudaSuccess || khz <= 0) khz = 1965000;
-    return ms * (long long)khz;
+    const long long cycles = ms * (long long)khz;
+    if (device >= 0 && device < 64) cache[device] = cycles;
+    return cycles;
 }
 
 double wall_seconds()

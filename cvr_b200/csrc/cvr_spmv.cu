@@ -219,9 +219,6 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
 
     // ---- per-warp TMA ring, set up once: the warp is persistent and walks chunks
     // warp0, warp0 + n_warps, ... (chunks are nnz-balanced, so a static round robin is even)
-    // iterated multi-GPU SpMV: the publish epilogue behind us is a programmatic dependent; let its
-    // blocks become resident as ours retire (it waits for this grid to complete before it reads y)
-    if (kPublish) asm volatile("griddepcontrol.launch_dependents;");
     const uint32_t ring = smem_u32(s_stream + w * G::WARP_SMEM);
     const uint32_t bar0 = smem_u32(&s_bar[w][0]);
     uint64_t policy = 0;
@@ -469,9 +466,10 @@ __device__ __forceinline__ void peer_flag_barrier(const CvrBarrier& b, int p)
 //   2. clear those rows of y again, ready for the next sweep (cvr_launch_spmv then skips its own
 //      clearing kernel);
 //   3. the last block to finish runs the all-to-all flag barrier over peer memory.
-// It is launched as a programmatic dependent of the sweep (its blocks are resident and waiting when
-// the sweep's last warp retires -- no launch gap), and the next iteration's sweep as a programmatic
-// dependent of it.
+// The next iteration's sweep is launched as a programmatic dependent of this kernel.  (Launching THIS
+// kernel as a programmatic dependent of the sweep as well was measured on 2 x B200, R-MAT-24: 991 us per
+// iteration against 893 us with an ordinary launch -- its early-resident blocks get in the sweep's way --
+// profiles/r02_bench_n2_pdl.txt; so it is an ordinary launch.)
 __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_t* __restrict__ boundary,
                                             int32_t n_boundary, const int32_t* __restrict__ empty,
                                             int32_t n_empty, const __grid_constant__ CvrPublish pub,
@@ -481,7 +479,6 @@ __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_
     // matrix stream) while this kernel publishes and waits at the barrier; it does not touch x or y
     // before its griddepcontrol.wait, i.e. before this grid -- barrier included -- has completed
     asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory"); // the sweep in front of us is complete and visible
     const bool publish_empty = (pub.mode & 2) == 0;
     const bool aliased = (pub.mode & 4) != 0;
     double* next_y = pub.clear_next ? pub.clear_next : y;
@@ -703,7 +700,7 @@ int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const
         const int cb = (n_clear + 255) / 256;
         const int cap = sms * 4;
         e = launch_ex(cvr_publish_epilogue_kernel, cb < cap ? (cb < 1 ? 1 : cb) : cap, 256, 0, stream,
-                      pdl && !ev_end, y, (const int32_t*)rows.boundary, rows.n_boundary,
+                      false, y, (const int32_t*)rows.boundary, rows.n_boundary,
                       (const int32_t*)rows.empty, rows.n_empty, *publish, *barrier, done_counter);
         if (e != cudaSuccess) return -1;
         launched++;
