@@ -677,8 +677,10 @@ def main():
     ap.add_argument("--no-subs", action="store_true", help="N = 1: skip the web / fem / road sub-records")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cusparse", action="store_true", help="skip the cuSPARSE CSR context measurement")
-    ap.add_argument("--row-weight", type=float, default=0.0,
-                    help="N > 1: balance shards by nnz + W per non-empty row instead of nnz alone (0 = nnz, the spec)")
+    ap.add_argument("--row-weight", type=float, default=None,
+                    help="N > 1: balance shards by nnz + W per non-empty row instead of nnz alone (0 = nnz, the spec). "
+                         "Default: 0 up to 4 GPUs, 4 from 8 GPUs on -- the cost model fitted to the measured per-rank "
+                         "sweep times on R-MAT-24 (profiles/r02_strong_scaling_rmat24.txt)")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="peer exchange: publish every row to every GPU instead of only to the GPUs that read it")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -693,6 +695,8 @@ def main():
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N > 1 with "
                          "`python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...`")
+    if args.row_weight is None:
+        args.row_weight = 4.0 if world >= 8 else 0.0
     if world == 1:
         run_single(args, local_rank)
     else:

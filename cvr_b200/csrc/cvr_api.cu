@@ -747,14 +747,14 @@ int cvr_column_footprint(cvr_handle_t* h, uint8_t* used_dev, void* cuda_stream)
     return CVR_OK;
 }
 
-int cvr_chunk_needs(cvr_handle_t* h, const uint8_t* needs_dev, uint8_t* chunk_any_dev, void* cuda_stream)
+int cvr_chunk_needs(cvr_handle_t* h, uint8_t* needs_dev, uint8_t* chunk_any_dev, void* cuda_stream)
 {
     if (!h || !needs_dev || !chunk_any_dev) return fail(CVR_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (cvr_launch_chunk_needs(h->chunks, h->n_chunks, needs_dev, chunk_any_dev,
+    if (cvr_launch_chunk_needs(h->chunks, h->n_chunks, h->rows, needs_dev, chunk_any_dev,
                                static_cast<cudaStream_t>(cuda_stream)) < 0)
         return fail(CVR_ERR_CUDA, "chunk-needs launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    h->launches += 1;
+    h->launches += 2;
     return CVR_OK;
 }
 

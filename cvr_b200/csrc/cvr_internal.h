@@ -45,7 +45,7 @@ __host__ __device__ inline int64_t cvr_segment_offset(int64_t chunk, int64_t fir
 struct CvrPublish {
     int32_t n_dst;                 // 0: do not publish
     int32_t self;                  // index of THIS GPU's own buffer in dst[] (used with mode bit 2)
-    int32_t mode;                  // bit 0: per-row stores at emit instead of the coalesced per-chunk push (A/B)
+    int32_t mode;                  // bit 0: reserved (round 1: per-row stores at emit)
                                    // bit 1: do not re-publish 0.0 for the never-written rows
                                    // bit 2: y IS this GPU's slice of the next x (no local copy; y[0] is foreign)
                                    // bit 3: no programmatic dependent launches (two shards share one device)
@@ -110,8 +110,8 @@ int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const
 int cvr_launch_peer_barrier(const CvrBarrier& b, cudaStream_t stream);
 // used[c] = 1 for every column id that occurs in cols[0..nnz)
 // chunk_any[t] = OR of needs[first_row..last_row] of chunk t
-int cvr_launch_chunk_needs(const CvrChunk* chunks, int32_t n_chunks, const uint8_t* needs, uint8_t* chunk_any,
-                           cudaStream_t stream);
+int cvr_launch_chunk_needs(const CvrChunk* chunks, int32_t n_chunks, const CvrRowLists& rows, uint8_t* needs,
+                           uint8_t* chunk_any, cudaStream_t stream);
 int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used, cudaStream_t stream);
 
 // sweep geometry for a matrix (index into the variant table of cvr_spmv.cu; CVR_SPMV_KERNEL overrides)

@@ -140,18 +140,33 @@ int64_t delim_at(const cvr_csr_t* csr, int64_t k)
 }
 
 // Cut points c[0..G] over the 1-based rows: part g owns rows c[g] .. c[g+1]-1 (c[0] = 1, c[G] = n_rows+1);
-// the cut for part g is the first ROW START at or after g * nnz / G, so no row straddles two devices.
-std::vector<int64_t> partition_rows_by_nnz(const cvr_csr_t* csr, int parts, int64_t last_delim)
+// the cut for part g is the first ROW START at or after g * W / G of the cumulative weight W, so no row
+// straddles two devices.  The weight of a row is its nnz (row_weight = 0, the north star's rule) or
+// nnz + row_weight if it is not empty: a finished row costs the sweep about as much as row_weight nonzeros
+// (record, y store, publishing), measured on R-MAT-24 (profiles/r02_strong_scaling_rmat24.txt).
+std::vector<int64_t> partition_rows_by_nnz(const cvr_csr_t* csr, int parts, int64_t last_delim, double row_weight)
 {
     std::vector<int64_t> cuts((size_t)parts + 1);
     cuts[0] = 1;
     cuts[(size_t)parts] = csr->n_rows + 1;
+    std::vector<int64_t> weighted; // weighted[k] = weight of rows < k, only built when row_weight != 0
+    if (row_weight > 0.0) {
+        weighted.resize((size_t)csr->n_rows + 2);
+        double extra = 0.0;
+        weighted[0] = 0;
+        for (int64_t k = 1; k <= csr->n_rows + 1; k++) {
+            if (delim_at(csr, k) > delim_at(csr, k - 1)) extra += row_weight;
+            weighted[(size_t)k] = delim_at(csr, k) + (int64_t)extra;
+        }
+    }
+    auto start_weight = [&](int64_t k) { return weighted.empty() ? delim_at(csr, k) : weighted[(size_t)k]; };
+    const int64_t total = weighted.empty() ? last_delim : weighted[(size_t)csr->n_rows + 1];
     for (int g = 1; g < parts; g++) {
-        const int64_t target = (last_delim * g) / parts;
-        int64_t lo = 1, hi = csr->n_rows + 1; // first k in [1, n_rows+1] with delim(k) >= target
+        const int64_t target = (total * g) / parts;
+        int64_t lo = 1, hi = csr->n_rows + 1; // first k in [1, n_rows+1] with start_weight(k) >= target
         while (lo < hi) {
             const int64_t mid = (lo + hi) / 2;
-            if (delim_at(csr, mid) >= target) hi = mid;
+            if (start_weight(mid) >= target) hi = mid;
             else lo = mid + 1;
         }
         cuts[(size_t)g] = std::min(std::max(lo, cuts[(size_t)g - 1]), csr->n_rows + 1);
@@ -369,7 +384,9 @@ int cvr_create_sharded(const cvr_csr_t* csr, int32_t n_chunks_per_device, const 
         view.row_delim32 = nullptr;
         view.row_delim64 = fixed.data();
     }
-    s->cuts = partition_rows_by_nnz(&view, n_devices, csr->nnz);
+    double row_weight = 0.0; // CVR_SHARD_ROW_WEIGHT: balance nnz + w per non-empty row instead of nnz alone
+    if (const char* e = getenv("CVR_SHARD_ROW_WEIGHT")) row_weight = atof(e);
+    s->cuts = partition_rows_by_nnz(&view, n_devices, csr->nnz, row_weight);
 
     int rc = CVR_OK;
     for (int g = 0; g < n_devices && rc == CVR_OK; g++) {

@@ -64,7 +64,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // same banks; padding each quarter separately needed 8 small copies per tile.)
 constexpr int WARPS = 4;              // warps per block
 constexpr int32_t WB_SPLIT0 = -2;     // marker: flush into the shared first row
-constexpr int32_t PUSH_MAX_ROWS = 1024; // widest row range a warp publishes as one contiguous push
+constexpr int32_t PUSH_MIN_ROWS = 64;   // a warp publishes finished rows to the peers in ranges of at least this many
 #ifndef CVR_TMA_STAGES
 #define CVR_TMA_STAGES 1
 #endif
@@ -84,7 +84,8 @@ struct TileCtx {
     double* __restrict__ y;
     const int32_t* tail;
     const CvrPublish* pub; // kernel parameter (constant bank); only read when kPublish
-    bool scatter;          // kPublish: publish row by row at emit (chunks whose row range is too wide)
+    int32_t last_done;     // kPublish: latest row this thread has stored in the current chunk (rows finish in order)
+    bool scatter;          // kPublish: rows of this chunk are mostly EMPTY: publish each finished row on its own
     int32_t split1, first_row;
     int l;
 };
@@ -101,27 +102,39 @@ __device__ __forceinline__ uint32_t publish_mask(const CvrPublish& pub, int32_t 
 
 // A finished row that this chunk owns alone: one plain store (spmv.cpp:1204).
 template <bool kPublish>
-__device__ __forceinline__ void store_row(const TileCtx& cx, int32_t row, double value)
+__device__ __forceinline__ void store_row(TileCtx& cx, int32_t row, double value)
 {
     cx.y[row] = value;
-    if (kPublish && cx.scatter) { // scattered 8-byte peer stores, row by row
-        const int64_t g = cx.pub->row_offset + row;
-        const uint32_t nb = publish_mask(*cx.pub, row);
+    if (kPublish) {
+        cx.last_done = row;
+        if (cx.scatter) { // 8-byte peer stores, row by row
+            const int64_t g = cx.pub->row_offset + row;
+            const uint32_t nb = publish_mask(*cx.pub, row);
 #pragma unroll
-        for (int p = 0; p < CVR_MAX_PEERS; p++)
-            if (p < cx.pub->n_dst && ((nb >> p) & 1u)) cx.pub->dst[p][g] = value;
+            for (int p = 0; p < CVR_MAX_PEERS; p++)
+                if (p < cx.pub->n_dst && ((nb >> p) & 1u)) cx.pub->dst[p][g] = value;
+        }
     }
 }
 
-// Iterated multi-GPU SpMV: when a warp has finished a chunk it publishes the chunk's whole row
-// range y[first_row .. last_row] -- contiguous, so the peer-mapped stores are coalesced 256 B
-// warp stores over NVLink -- into the x vector every GPU reads in the NEXT iteration.  The transfer
-// thus runs chunk by chunk inside the SpMV kernel, overlapped with the other warps' sweeps.  Rows of
-// the range that are still being accumulated (shared first/last rows, tail rows) are sent as they
-// are and overwritten by cvr_publish_rows_kernel once the sweep is complete (same source GPU, same
-// address, stream order); empty rows carry the 0.0 the clearing kernel put there.
-__device__ __forceinline__ void publish_chunk_rows(const TileCtx& cx, int32_t first_row, int32_t last_row,
-                                                   int t)
+// Iterated multi-GPU SpMV: the rows a warp has FINISHED are published -- stored into the x vector every GPU
+// reads in the NEXT iteration -- from inside the sweep, range by range, while the warp is still walking its
+// chunk: contiguous rows, so the peer-mapped stores are coalesced 256 B warp stores over NVLink, and the
+// transfer overlaps the sweep tile by tile.  Which rows are finished: the conversion hands rows to the eight
+// SIMD lanes in increasing order and a lane works through its rows one after the other, so every row up to
+// min over the lanes of (the latest row that lane has stored) is complete or empty -- the watermark the
+// tile loop maintains with five shuffles per tile.  (Round 1 pushed a chunk's whole range at its end and fell
+// back to per-row 8-byte peer stores for chunks spanning more than 1024 rows; on R-MAT-24 over 8 GPUs those
+// scattered stores doubled the sweep of the row-heavy ranks, profiles/r02_strong_scaling_v1.txt.)
+// Rows of a range that are still being accumulated (shared first/last rows, tail rows) are sent as they are
+// and overwritten by the epilogue kernel once the sweep is complete (same source GPU, same address, stream
+// order); empty rows are skipped (their `needs` byte is cleared, cvr_chunk_needs) -- the epilogue zeroes them
+// everywhere during the first two iterations.
+// Exception: a chunk in a very sparse region spans 10^4..10^6 rows of which a few hundred are not empty;
+// walking such a range row by row costs more than it saves (measured: the row-heavy shard of R-MAT-24 on
+// 2 GPUs went from 883 to 1304 us), so a chunk whose row span exceeds 4x the rows it finishes publishes
+// each finished row on its own at the moment it is stored (`scatter`).
+__device__ __forceinline__ void publish_rows(const TileCtx& cx, int32_t first_row, int32_t last_row, int t)
 {
     __threadfence_block(); // this warp's own row stores (made by other lanes) before the re-read
     __syncwarp();
@@ -132,8 +145,8 @@ __device__ __forceinline__ void publish_chunk_rows(const TileCtx& cx, int32_t fi
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const bool in = r0 + 32 * u <= last_row;
-            v[u] = in ? __ldcg(cx.y + r0 + 32 * u) : 0.0;
             nb[u] = !in ? 0u : publish_mask(pub, r0 + 32 * u);
+            v[u] = nb[u] ? __ldcg(cx.y + r0 + 32 * u) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -146,7 +159,7 @@ __device__ __forceinline__ void publish_chunk_rows(const TileCtx& cx, int32_t fi
 }
 
 template <bool kPublish>
-__device__ __forceinline__ void emit(const TileCtx& cx, double value, int32_t pos, int32_t wb,
+__device__ __forceinline__ void emit(TileCtx& cx, double value, int32_t pos, int32_t wb,
                                      double& carry_slot)
 {
     if (wb >= 0 && pos <= cx.split1) store_row<kPublish>(cx, wb, value);   // feeding, :1204 (split1 = -1: never)
@@ -243,14 +256,15 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
         cx.y = y;
         cx.tail = cp->tail;
         cx.pub = &pub;
-        // A chunk in a very sparse region can span 10^5 (mostly empty) rows: pushing that range from
-        // one warp would serialise; such chunks publish their few finished rows one by one instead
-        // (their empty rows get their 0.0 from cvr_publish_rows_kernel either way).
         const int32_t chunk_last_row = cp->last_row;
-        cx.scatter = kPublish && ((pub.mode & 1) || chunk_last_row - cp->first_row >= PUSH_MAX_ROWS);
+        const bool reads_elsewhere = kPublish && (!pub.chunk_any || pub.chunk_any[chunk]); // a peer reads some row
+        cx.scatter = reads_elsewhere && (chunk_last_row - cp->first_row + 1 > 4 * (n_rec + CVR_W));
+        const bool publishing = reads_elsewhere && !cx.scatter; // range pushes behind the watermark
+        int32_t pushed_upto = cp->first_row; // kPublish: first row of the chunk not yet sent to the peers
         cx.split1 = cp->split1;
         cx.first_row = cp->first_row;
         cx.l = l;
+        cx.last_done = cp->first_row - 1;
 
         const int2* rec = reinterpret_cast<const int2*>(record + cvr_record_offset(chunk, cx.first_row));
         const double* v = vals + start;
@@ -395,6 +409,19 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
             lane_carry = __shfl_sync(FULL, out, 24 + l);
             if (has) emit<kPublish>(cx, head + cin, p0 + b_first * CVR_W, s_wb[w][b_first][t], carry_slot);
             __syncwarp(); // slots are reused by the next tile's delivery
+            if (kPublish && publishing) {
+                // watermark: every row up to min over the SIMD lanes of the lane's latest stored row is final
+                int32_t f = cx.last_done;
+                f = max(f, __shfl_xor_sync(FULL, f, 8));
+                f = max(f, __shfl_xor_sync(FULL, f, 16)); // latest row of SIMD lane l (any of its four walkers)
+                f = min(f, __shfl_xor_sync(FULL, f, 1));
+                f = min(f, __shfl_xor_sync(FULL, f, 2));
+                f = min(f, __shfl_xor_sync(FULL, f, 4));
+                if (f - pushed_upto + 1 >= PUSH_MIN_ROWS) {
+                    publish_rows(cx, pushed_upto, f, t);
+                    pushed_upto = f + 1;
+                }
+            }
         }
 
         // ---- chunk epilogue: lane remainders through the eight pos=-1 records (spmv.cpp:1633-1649)
@@ -411,8 +438,8 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
             const int32_t row = cp->tail[t];
             if (row != 0) atomicAdd(&y[row], carry); // row 0 = phantom row of unused lanes (carry 0.0)
         }
-        if (kPublish && !cx.scatter && (!pub.chunk_any || pub.chunk_any[chunk]))
-            publish_chunk_rows(cx, cx.first_row, chunk_last_row, t);
+        if (kPublish && publishing && pushed_upto <= chunk_last_row)
+            publish_rows(cx, pushed_upto, chunk_last_row, t); // what the watermark had not reached
     }
 }
 
@@ -496,7 +523,9 @@ __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_
             next_y[row] = 0.0;
         }
         const int64_t g = pub.row_offset + row;
-        const uint32_t nb = publish_mask(pub, row);
+        // never-written rows: their `needs` byte is cleared (the sweep's range pushes skip them), so the
+        // explicit 0.0 of the first two iterations goes to every destination but the own aliased buffer
+        const uint32_t nb = b ? publish_mask(pub, row) : ((pub.mode & 4) ? (0xffu & ~(1u << pub.self)) : 0xffu);
 #pragma unroll
         for (int p = 0; p < CVR_MAX_PEERS; p++)
             if (p < pub.n_dst && ((nb >> p) & 1u)) pub.dst[p][g] = v;
@@ -719,6 +748,12 @@ __global__ void cvr_column_footprint_kernel(const int32_t* __restrict__ cols, in
 } // namespace
 
 namespace {
+__global__ void cvr_clear_needs_kernel(const int32_t* __restrict__ empty, int32_t n_empty, uint8_t* __restrict__ needs)
+{
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_empty; i += gridDim.x * blockDim.x)
+        needs[empty[i]] = 0;
+}
+
 __global__ void cvr_chunk_needs_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
                                        const uint8_t* __restrict__ needs, uint8_t* __restrict__ chunk_any)
 {
@@ -732,11 +767,17 @@ __global__ void cvr_chunk_needs_kernel(const CvrChunk* __restrict__ chunks, int3
 }
 } // namespace
 
-int cvr_launch_chunk_needs(const CvrChunk* chunks, int32_t n_chunks, const uint8_t* needs, uint8_t* chunk_any,
-                           cudaStream_t stream)
+int cvr_launch_chunk_needs(const CvrChunk* chunks, int32_t n_chunks, const CvrRowLists& rows, uint8_t* needs,
+                           uint8_t* chunk_any, cudaStream_t stream)
 {
+    // rows nothing ever writes are published once by the epilogue (an explicit 0.0 during the first two
+    // iterations), never by the sweep: drop them from the footprint the range pushes consult
+    if (rows.n_empty > 0) {
+        const int blocks = (rows.n_empty + 255) / 256;
+        cvr_clear_needs_kernel<<<blocks < 4096 ? blocks : 4096, 256, 0, stream>>>(rows.empty, rows.n_empty, needs);
+    }
     cvr_chunk_needs_kernel<<<(n_chunks * 32 + 127) / 128, 128, 0, stream>>>(chunks, n_chunks, needs, chunk_any);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
 int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used, cudaStream_t stream)
@@ -765,5 +806,6 @@ void cvr_preload_spmv_kernels()
     cudaFuncGetAttributes(&a, cvr_peer_barrier_kernel);
     cudaFuncGetAttributes(&a, cvr_column_footprint_kernel);
     cudaFuncGetAttributes(&a, cvr_chunk_needs_kernel);
+    cudaFuncGetAttributes(&a, cvr_clear_needs_kernel);
 }
 

@@ -156,7 +156,7 @@ int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* c
 typedef struct cvr_publish {
     int32_t n_dst;       /* 1..CVR_MAX_PEERS destinations, own buffer included */
     int32_t self;        /* index of this GPU's own buffer in dst[] (required with mode bit 2) */
-    int32_t mode;        /* bit 0: per-row stores instead of the coalesced per-chunk push (A/B);
+    int32_t mode;        /* bit 0: reserved;
                             bit 1: skip the 0.0 for never-written rows (set from the 3rd iteration on);
                             bit 3: no programmatic dependent launches (set when one device carries two shards);
                             bit 2: y_dev IS this GPU's own slice of the next x (x_next + row_offset), so
@@ -187,8 +187,10 @@ int cvr_check_async_error(cvr_handle_t* h);
  * GPU actually reads.  Exchanged once, it lets every GPU publish a row only to the peers that
  * read it (a banded matrix then sends halos, not the whole vector). */
 int cvr_column_footprint(cvr_handle_t* h, uint8_t* used_dev, void* cuda_stream);
-/* chunk_any_dev[t] (n_chunks bytes) = OR of needs_dev over the row range of chunk t */
-int cvr_chunk_needs(cvr_handle_t* h, const uint8_t* needs_dev, uint8_t* chunk_any_dev, void* cuda_stream);
+/* Finishes a footprint for cvr_spmv_publish: clears needs_dev[row] for the rows nothing ever writes (the
+ * epilogue publishes their 0.0, the sweep's range pushes skip them), then chunk_any_dev[t] (n_chunks bytes)
+ * = OR of needs_dev over the row range of chunk t. */
+int cvr_chunk_needs(cvr_handle_t* h, uint8_t* needs_dev, uint8_t* chunk_any_dev, void* cuda_stream);
 int cvr_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char handle[64]); /* zero-filled */
 int cvr_peer_open(int device, const unsigned char handle[64], void** dev_ptr);
 int cvr_peer_close(int device, void* dev_ptr);
