@@ -43,7 +43,10 @@ def main():
         del rows, prod, rd
         nnz_true = d.nnz_true
         for variant in args.variants.split(","):
-            os.environ[args.env] = variant
+            if variant == "auto":  # the per-matrix choice of the library
+                os.environ.pop(args.env, None)
+            else:
+                os.environ[args.env] = variant
             m = cvr_b200.CvrMatrix(d, args.chunks, 0)
             info = m.info
             y = torch.empty(n + 1, dtype=torch.float64, device=dev)
@@ -67,7 +70,7 @@ def main():
             ksecs, kl = m.kernel_timing()
             m.set_kernel_timing(False)
             kus = ksecs / max(kl, 1) * 1e6
-            rec = {"workload": name, "variant": variant, "chunks": info["n_chunks"], "kernel_us": kus,
+            rec = {"workload": name, "variant": variant, "kernel": m.kernel_name, "chunks": info["n_chunks"], "kernel_us": kus,
                    "step_us": step_ms / args.steps * 1e3, "gflops": 2.0 * nnz_true / (kus * 1e-6) / 1e9,
                    "frac": info["algorithmic_bytes"] / (kus * 1e-6) / 1e9 / peak, "rows_failing": bad}
             line = json.dumps(rec)
