@@ -90,6 +90,8 @@ struct cvr_handle {
     unsigned int* done_counter = nullptr; // [0] last-block detection of the publish epilogue,
                                           // [1] epoch of the first peer barrier that timed out (0 = none)
     // CUDA graph of GRAPH_UNROLL iterations of the host-facing loop (cvr_spmv with iters >> 1): captured once
+    cudaStream_t copy_stream = nullptr;          // D2H of finished row slabs behind the sweep (cvr_spmv, iters = 1)
+    std::vector<cudaEvent_t> slab_events;
     cudaGraphExec_t loop_graph = nullptr;
     int loop_graph_variant = -1; // sweep geometry the graph was captured with (CVR_SPMV_KERNEL can change it)
     int64_t loop_graph_kernels = 0;
@@ -101,6 +103,8 @@ struct cvr_handle {
     {
         cudaSetDevice(device);
         if (loop_graph) cudaGraphExecDestroy(loop_graph);
+        for (cudaEvent_t e : slab_events) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         cudaFree(vals);
         cudaFree(cols);
         cudaFree(record);
@@ -568,6 +572,59 @@ int cvr_spmv(cvr_handle_t* h, const double* x_host, double* y_host, int32_t iter
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(h->x, x_host, sizeof(double) * (size_t)(h->n_cols + 1),
                              cudaMemcpyHostToDevice, h->stream));
+    // ---- one SpMV with host vectors: pipeline the sweep and the copy of y.  The chunks are swept in SLABS
+    // (one launch each, same kernel); when a slab is done every row before the first row of the next slab is
+    // final, so its part of y goes back over PCIe on a second stream while the next slab is swept.  On
+    // R-MAT-24 (134 MB of y, 2.4 ms over PCIe against a 1.4 ms sweep) that hides the sweep behind the copy.
+    {
+        constexpr int32_t SLABS = 8;
+        const char* ns = getenv("CVR_NO_SLABS");
+        const size_t y_bytes = sizeof(double) * (size_t)(h->n_rows + 1);
+        size_t min_bytes = (size_t)8 << 20; // below this the extra launches cost more than the overlap gains
+        if (const char* mb = getenv("CVR_SLAB_MIN_BYTES")) min_bytes = (size_t)atoll(mb);
+        if (iters == 1 && !h->timing && !(ns && *ns == '1') && y_bytes >= min_bytes &&
+            h->n_chunks >= 64 * SLABS) {
+            if (!h->copy_stream) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+                for (int k = 0; k < SLABS; k++) {
+                    cudaEvent_t e;
+                    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    h->slab_events.push_back(e);
+                }
+            }
+            CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+            int64_t copied_upto = 0; // rows [0, copied_upto) are on their way to the host
+            for (int32_t k = 0; k < SLABS; k++) {
+                const int32_t c0 = (int32_t)((int64_t)h->n_chunks * k / SLABS);
+                const int32_t c1 = (int32_t)((int64_t)h->n_chunks * (k + 1) / SLABS);
+                const int launched = cvr_launch_spmv(h->variant, h->chunks, h->n_chunks, h->vals, h->cols, h->record, h->x,
+                                                     h->y, h->n_rows, h->rows, nullptr, h->stream, nullptr, nullptr,
+                                                     nullptr, nullptr, /*y_is_clear=*/k > 0, c0, c1);
+                if (launched < 0)
+                    return fail(CVR_ERR_CUDA, "SpMV launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                h->launches += launched;
+                CUDA_TRY(cudaEventRecord(h->slab_events[(size_t)k], h->stream));
+                // the first row of the next slab may still be accumulated by it: stop one row short
+                const int64_t final_upto = k + 1 < SLABS ? (int64_t)h->host_chunks[(size_t)c1].first_row : h->n_rows + 1;
+                if (final_upto > copied_upto) {
+                    CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->slab_events[(size_t)k], 0));
+                    CUDA_TRY(cudaMemcpyAsync(y_host + copied_upto, h->y + copied_upto,
+                                             sizeof(double) * (size_t)(final_upto - copied_upto), cudaMemcpyDeviceToHost,
+                                             h->copy_stream));
+                    copied_upto = final_upto;
+                }
+            }
+            CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+            if (seconds_per_iter) {
+                float ms = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+                *seconds_per_iter = (double)ms * 1e-3;
+            }
+            return CVR_OK;
+        }
+    }
     // The iteration loop (the reference's spmv.cpp:1024-1034).  From GRAPH_UNROLL iterations on it is replayed
     // from a CUDA graph captured once per handle: GRAPH_UNROLL x (clearing kernel -> sweep, programmatic edge
     // kept) per graph launch instead of two launches per iteration.  CVR_NO_GRAPH=1 keeps the plain loop.

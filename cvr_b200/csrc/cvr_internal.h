@@ -100,13 +100,14 @@ int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t*
 int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream);
 // repairs the reference's off-by-one trailing delimiters (nnz-1 -> nnz) in a DEVICE delimiter array we own
 int cvr_launch_fix_last_delim(int32_t* rd32, int64_t* rd64, int64_t n_rows, int64_t nnz, cudaStream_t stream);
-// ev_begin / ev_end (optional) bracket the SpMV kernel alone, after y has been cleared
+// ev_begin / ev_end (optional) bracket the SpMV kernel alone, after y has been cleared;
+// [chunk_begin, chunk_end) restricts the sweep to a slab of chunks (chunk_end < 0: through the last chunk)
 int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const double* vals,
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
                     int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
                     cudaStream_t stream, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr,
                     const CvrBarrier* barrier = nullptr, unsigned int* done_counter = nullptr,
-                    bool y_is_clear = false);
+                    bool y_is_clear = false, int32_t chunk_begin = 0, int32_t chunk_end = -1);
 int cvr_launch_peer_barrier(const CvrBarrier& b, cudaStream_t stream);
 // used[c] = 1 for every column id that occurs in cols[0..nnz)
 // chunk_any[t] = OR of needs[first_row..last_row] of chunk t

@@ -213,7 +213,7 @@ __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return ((w * 0x0
 
 template <int TB, int NB, bool kPublish>
 __global__ void __launch_bounds__(WARPS * 32, NB)
-cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
+cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, int32_t T,
                      const double* __restrict__ vals, const int32_t* __restrict__ cols,
                      const int32_t* __restrict__ record, const double* __restrict__ x,
                      double* __restrict__ y, const __grid_constant__ CvrPublish pub)
@@ -246,7 +246,8 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t T,
     for (int k = 0; k < FLAG_WORDS; k++) s_flags[w][k][t] = 0u;
     __syncwarp();
 
-    for (int32_t chunk = warp0; chunk < T; chunk += n_warps) {
+    // chunks [chunk_begin, T) of the matrix (the whole matrix unless the host pipelines the sweep in slabs)
+    for (int32_t chunk = chunk_begin + warp0; chunk < T; chunk += n_warps) {
         const CvrChunk* cp = chunks + chunk;
         const int64_t start = cp->start;
         const int32_t len = cp->len;
@@ -602,14 +603,15 @@ struct TileOps {
         return blocks;
     }
     static cudaError_t launch(bool publish, int blocks, cudaStream_t stream, bool programmatic,
-                              const CvrChunk* chunks, int32_t T, const double* vals, const int32_t* cols,
-                              const int32_t* record, const double* x, double* y, const CvrPublish& pub)
+                              const CvrChunk* chunks, int32_t chunk_begin, int32_t chunk_end, const double* vals,
+                              const int32_t* cols, const int32_t* record, const double* x, double* y,
+                              const CvrPublish& pub)
     {
         if (publish)
             return launch_ex(cvr_spmv_tile_kernel<TB, NB, true>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
-                             programmatic, chunks, T, vals, cols, record, x, y, pub);
+                             programmatic, chunks, chunk_begin, chunk_end, vals, cols, record, x, y, pub);
         return launch_ex(cvr_spmv_tile_kernel<TB, NB, false>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
-                         programmatic, chunks, T, vals, cols, record, x, y, pub);
+                         programmatic, chunks, chunk_begin, chunk_end, vals, cols, record, x, y, pub);
     }
     static void preload()
     {
@@ -686,8 +688,10 @@ int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
                     int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
                     cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end,
-                    const CvrBarrier* barrier, unsigned int* done_counter, bool y_is_clear)
+                    const CvrBarrier* barrier, unsigned int* done_counter, bool y_is_clear,
+                    int32_t chunk_begin, int32_t chunk_end)
 {
+    if (chunk_end < 0) chunk_end = n_chunks;
     int launched = 0;
     const int f = forced_variant();
     const int v = f >= 0 ? f : variant;
@@ -707,7 +711,7 @@ int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const
         return -1;
     }
     const int threads = WARPS * 32;
-    const int blocks = (int)(((int64_t)n_chunks * 32 + threads - 1) / threads);
+    const int blocks = (int)(((int64_t)(chunk_end - chunk_begin) * 32 + threads - 1) / threads);
     // the sweeps are persistent: one block per resident slot, warps stride over the chunks
     const int resident = sms * variant_resident_blocks(v);
     const int pblocks = blocks < resident ? blocks : resident;
@@ -719,8 +723,8 @@ int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const
     const bool programmatic = pdl && (after_clear_kernel || (pub && y_is_clear)) && !ev_begin;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
     cudaError_t e = cudaSuccess;
-    CVR_FOR_VARIANT(v, e = P::launch(pub, pblocks, stream, programmatic, chunks, n_chunks, vals, cols, record, x, y,
-                                     pub ? *publish : none))
+    CVR_FOR_VARIANT(v, e = P::launch(pub, pblocks, stream, programmatic, chunks, chunk_begin, chunk_end, vals, cols,
+                                     record, x, y, pub ? *publish : none))
     if (e != cudaSuccess) return -1;
     launched++;
     if (ev_end) cudaEventRecord(ev_end, stream);

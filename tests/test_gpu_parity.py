@@ -165,6 +165,26 @@ def test_iteration_loop_replayed_from_a_cuda_graph(cvr, monkeypatch):
         assert_y_close(y_again, csr, 2.0 * x, "graph loop, second x")
 
 
+def test_single_spmv_pipelined_in_slabs(cvr, monkeypatch):
+    """cvr_spmv with iters = 1 sweeps the chunks in 8 slabs and copies the finished rows of y back behind each
+    slab (large matrices only by default; forced here): same y, also when slabs cut through shared rows, long
+    rows spanning several slabs and empty rows."""
+    from cvr_b200 import gen
+    monkeypatch.setenv("CVR_SLAB_MIN_BYTES", "0")
+    for d in (gen.random_sparse(30000, 30000, 200000, seed=53, empty_frac=0.3, long_rows=3, long_len=20000),
+              gen.rmat(14, 16, seed=54), gen.road(100000, seed=55)):
+        csr = to_oracle_csr(d)
+        x = np.random.default_rng(13).uniform(-1, 1, csr.n_cols + 1)
+        for T in (512, 3000):
+            with cvr.CvrMatrix(d.to_host(), T) as m:
+                l0 = m.info["kernel_launches"]
+                y, secs = m.spmv(x, iters=1)
+                assert m.info["kernel_launches"] - l0 == 9 and secs > 0  # one clearing kernel + 8 slabs
+                assert_y_close(y, csr, x, f"slabs T={T}")
+                y2, _ = m.spmv(x, iters=2)  # the plain loop on the same handle
+                assert_y_close(y2, csr, x, f"after slabs T={T}")
+
+
 def test_save_load_round_trip(cvr, tmp_path):
     """cvr_save / cvr_load: the reloaded matrix exports the same structure bit for bit and gives the
     same y (conversion skipped)."""
