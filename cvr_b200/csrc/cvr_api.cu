@@ -207,7 +207,19 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
         return fail(CVR_ERR_CUDA, "cudaMalloc(seg_count): %s", cudaGetErrorString(e));
     }
 
+    uint32_t* row_bitmap = nullptr;
+    const size_t bitmap_words = (size_t)(h->n_rows + 2) / 32 + 2;
+    e = cudaMalloc(reinterpret_cast<void**>(&row_bitmap), sizeof(uint32_t) * bitmap_words);
+    if (e == cudaSuccess) e = cudaMemsetAsync(row_bitmap, 0, sizeof(uint32_t) * bitmap_words, h->stream);
+    if (e != cudaSuccess) {
+        cudaFree(segments);
+        cudaFree(seg_count);
+        cudaFree(row_bitmap);
+        return fail(CVR_ERR_CUDA, "cudaMalloc(row_bitmap): %s", cudaGetErrorString(e));
+    }
+
     CvrConvertArgs a{};
+    a.row_bitmap = row_bitmap;
     a.csr_val = csr->val;
     a.csr_col = csr->col;
     a.rd32 = csr->row_delim32;
@@ -258,6 +270,7 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
     } while (0);
     cudaFree(segments);
     cudaFree(seg_count);
+    cudaFree(row_bitmap);
     if (rc != CVR_OK) return rc;
     if (e != cudaSuccess) return fail(CVR_ERR_CUDA, "conversion failed: %s", cudaGetErrorString(e));
     h->convert_kernel_seconds = ms_kernels * 1e-3;

@@ -262,6 +262,244 @@ cvr_schedule_warp_kernel(const RdT* __restrict__ rd, int64_t nnz, int64_t n_rows
   } // next chunk of this warp
 }
 
+// ---------------------------------------------------------------------------------------
+// cvr_schedule_group_kernel -- the same greedy schedule with EIGHT THREADS per chunk (the default).
+//
+// The warp-per-chunk kernel above is instruction-bound, not memory-bound: ncu on the road matrix shows 76 %
+// issue utilisation, 1.86 G warp instructions = 262 per event step, of which only the 8 tracker lanes do
+// useful work (profiles/r02_prof_schedule_road_summary.txt).  Here a chunk is scheduled by one 8-thread
+// group -- thread l IS SIMD lane l, the scalar state is replicated in the group -- so a warp advances FOUR
+// chunks with the same instruction stream.  What replaced the 32-entry delimiter window of the warp kernel:
+//   * a bitmap of the non-empty rows (cvr_row_bitmap_kernel, one pass over the delimiters: n_rows / 8 bytes)
+//     -- "the next k non-empty rows at or after next_row" is a 32-bit window of it (funnel shift of two
+//     words) plus a select-the-n-th-set-bit; rows that lie further ahead fall back to the one-lane path;
+//   * the two delimiters of a row a lane is fed are loaded directly (the group touches neighbouring rows:
+//     L1 hits).
+// All votes, shuffles and reductions use the group's own member mask, so the four groups of a warp may
+// diverge (different step counts, a group in the stealing path); control flow inside a group is uniform.
+// Same reference lines as the warp kernel; bit-exact on the same suite.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int nth_set_bit(uint32_t w, int n) // position of the n-th (0-based) set bit, n < popc(w)
+{
+    int pos = 0;
+    int c = __popc(w & 0xffffu);
+    if (n >= c) { n -= c; pos += 16; w >>= 16; }
+    c = __popc(w & 0xffu);
+    if (n >= c) { n -= c; pos += 8; w >>= 8; }
+    c = __popc(w & 0xfu);
+    if (n >= c) { n -= c; pos += 4; w >>= 4; }
+    c = __popc(w & 0x3u);
+    if (n >= c) { n -= c; pos += 2; w >>= 2; }
+    if (n >= (int)(w & 1u)) pos += 1;
+    return pos;
+}
+
+// bit r of the bitmap: row r holds at least one element (rows 0 .. n_rows+1; the array has one spare word)
+template <typename RdT>
+__global__ void cvr_row_bitmap_kernel(const RdT* __restrict__ rd, int64_t n_rows, uint32_t* __restrict__ bitmap)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool nz = r <= n_rows && rd[r + 1] != rd[r];
+    const unsigned word = __ballot_sync(FULL, nz);
+    if ((threadIdx.x & 31) == 0 && (r >> 5) <= (n_rows + 2) / 32 + 1) bitmap[r >> 5] = word;
+}
+
+template <typename RdT>
+__global__ void __launch_bounds__(128)
+cvr_schedule_group_kernel(const RdT* __restrict__ rd, const uint32_t* __restrict__ bitmap, int64_t nnz,
+                          int64_t n_rows, int32_t T, int32_t* __restrict__ record, CvrChunk* __restrict__ chunks,
+                          int2* __restrict__ segments, int32_t* __restrict__ seg_count)
+{
+    const int l = threadIdx.x & 7;                    // my SIMD lane
+    const int gshift = threadIdx.x & 24;              // first lane of my group inside the warp
+    const unsigned gmask = 0xffu << gshift;           // member mask of my group
+    const unsigned lt = (1u << l) - 1u;               // SIMD lanes before mine
+    const int32_t n_groups = (gridDim.x * blockDim.x) >> 3;
+    auto gballot = [&](bool p) { return (__ballot_sync(gmask, p) >> gshift) & 0xffu; };
+    // rows r .. r+31 of the bitmap as one word (bit j: row r + j is not empty)
+    auto window = [&](int64_t r) {
+        const int64_t w = r >> 5;
+        return __funnelshift_r(bitmap[w], bitmap[w + 1], (unsigned)(r & 31));
+    };
+    const int64_t per = (nnz / T / 16) * 16;
+    const int64_t brk = (nnz - per * T) / 16;
+
+  for (int32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; chunk < T; chunk += n_groups) {
+    int64_t s, e; // nnz-balanced slice of this chunk, multiples of 16 (spmv.cpp:584-586, :615-627)
+    if (chunk < brk) {
+        s = chunk * (per + 16);
+        e = (chunk + 1) * (per + 16);
+    } else {
+        s = chunk * per + brk * 16;
+        e = (chunk + 1) * per + brk * 16;
+    }
+    if (chunk == T - 1) e = nnz;
+    const int64_t r0 = last_row_not_after(rd, 0, n_rows, s);        // :631-650
+    int64_t r1 = last_row_not_after(rd, r0, n_rows, e - 1);         // :652-667
+    while (r1 <= n_rows && rd[r1 + 1] == rd[r1]) r1++;              // :687-688 (degenerate tails only)
+    const int64_t span = r1 - r0 + 1;
+    const int32_t len = (int32_t)(e - s);
+    const int32_t n_steps = len / CVR_W;
+
+    int2* rec = reinterpret_cast<int2*>(record + cvr_record_offset(chunk, r0));
+    int2* seg = segments + cvr_segment_offset(chunk, r0);
+    int32_t n_rec = 0, n_seg = 0;
+
+    // lane trackers (vPack_valID / rowID / count / flag, :711-759): lane l starts on row r0 + l, empty or not
+    int32_t src = 0, row = 0, left = 0, from = -1;
+    {
+        const int64_t my_row = r0 + l;
+        if (my_row <= r1) {
+            const int64_t a = (int64_t)rd[my_row], b = (int64_t)rd[my_row + 1];
+            src = (int32_t)(a - s);
+            row = (int32_t)my_row;
+            left = my_row < r1 ? (int32_t)(b - a) : (int32_t)(e - a);
+            if (l == 0) { // the first row may have begun in the previous chunk
+                src = 0;
+                left = my_row == r1 ? len : (int32_t)(b - s);
+            }
+        }
+    }
+    int64_t next_row = r0 + CVR_W;
+    unsigned stolen = 0, dirty = 0xffu;
+    bool tail_stored = false, stealing = false;
+    int32_t split0 = 0, split1 = 0, tail = 0;
+
+    int32_t i = 0;
+    while (i < n_steps) {
+        unsigned zero_mask = gballot(left == 0);
+        if (zero_mask && next_row < r1) {
+            // ---- fast path: feed ALL lanes that ran empty at this step in one pass: in lane order they take
+            // the next non-empty rows, i.e. the j-th empty lane gets the j-th set bit of the window.  Only rows
+            // strictly before r1 qualify (feeding r1 snapshots the tail, :844-857) and all of them must lie
+            // inside the 32-row window; otherwise the one-lane path below handles the step.
+            unsigned w = window(next_row);
+            if (r1 - next_row < 32) w &= (1u << (int)(r1 - next_row)) - 1u;
+            const int k = __popc(zero_mask);
+            if (__popc(w) >= k) {
+                const bool mine = (zero_mask >> l) & 1u;
+                const int bit = mine ? nth_set_bit(w, __popc(zero_mask & lt)) : 0;
+                const int64_t new_row = next_row + bit;
+                int64_t a0 = 0, a1 = 0;
+                if (mine) {
+                    a0 = (int64_t)rd[new_row];
+                    a1 = (int64_t)rd[new_row + 1];
+                }
+                const unsigned first_mask = gballot(mine && row == (int32_t)r0); // <= 1 lane
+                if (first_mask) split0 = i * CVR_W + (__ffs(first_mask) - 1);    // :826-829
+                const unsigned rec_mask = zero_mask & ~first_mask;
+                if (mine && !((first_mask >> l) & 1u))
+                    rec[n_rec + __popc(rec_mask & lt)] = make_int2(i * CVR_W + l, row); // :832-834
+                n_rec += __popc(rec_mask);
+                if (mine) {
+                    src = (int32_t)(a0 - s);
+                    row = (int32_t)new_row;
+                    left = (int32_t)(a1 - a0);
+                }
+                next_row += nth_set_bit(w, k - 1) + 1;
+                dirty |= zero_mask;
+                zero_mask = 0;
+            }
+        }
+        while (zero_mask) {
+            const int z = __ffs(zero_mask) - 1; // the empty lane handled now, in lane order (:814-816)
+            zero_mask &= zero_mask - 1;
+            const int32_t pos = i * CVR_W + z;
+            if (next_row <= r1) {
+                // ---- feeding (:821-868)
+                const int32_t row_z = __shfl_sync(gmask, row, gshift + z);
+                if (row_z == (int32_t)r0) split0 = pos;
+                else {
+                    if (l == 0) rec[n_rec] = make_int2(pos, row_z);
+                    n_rec++;
+                }
+                for (;;) { // next non-empty row at or after next_row (row r1 is not empty)
+                    const unsigned w = window(next_row);
+                    if (w) {
+                        next_row += __ffs(w) - 1;
+                        break;
+                    }
+                    next_row += 32;
+                }
+                const int64_t a = (int64_t)rd[next_row], b = (int64_t)rd[next_row + 1];
+                if (l == z) {
+                    src = (int32_t)(a - s);
+                    row = (int32_t)next_row;
+                    left = (int32_t)(b - a);
+                    if (next_row == r1) left = (int32_t)(e - a);
+                }
+                if (next_row == r1) {
+                    if (split1 == 0) split1 = pos;
+                    tail = row;
+                    tail_stored = true;
+                    if (left == 0) from = 0; // :855-856
+                }
+                next_row++;
+            } else {
+                // ---- stealing (:869-943): split the first lane that holds more than the average
+                const int32_t total = __reduce_add_sync(gmask, left);
+                const int32_t ave = total / CVR_W;
+                const unsigned richer = gballot(left > ave);
+                const int victim = richer ? __ffs(richer) - 1 : CVR_W - 1;
+                const int32_t from_z = __shfl_sync(gmask, from, gshift + z);
+                if (!((stolen >> z) & 1u)) {
+                    if (!stealing) {
+                        if (split1 == 0) split1 = (span <= CVR_W) ? -1 : pos;
+                        tail = row;
+                        tail_stored = true;
+                        stealing = true;
+                    }
+                    if (l == 0) rec[n_rec] = make_int2(pos, z);
+                    stolen |= 1u << z;
+                } else {
+                    if (l == 0) rec[n_rec] = make_int2(pos, from_z); // :904-909, unreachable
+                }
+                n_rec++;
+                const int32_t vsrc = __shfl_sync(gmask, src, gshift + victim);
+                if (l == z) {
+                    from = victim;
+                    src = vsrc;
+                    row = victim;
+                    left = ave;
+                }
+                if (l == victim) {
+                    left -= ave;
+                    src += ave;
+                }
+                dirty |= 1u << victim;
+            }
+            dirty |= 1u << z;
+        }
+        // ---- one segment entry per lane that changed its source at this step
+        if ((dirty >> l) & 1u) seg[n_seg + __popc(dirty & lt)] = make_int2(i * CVR_W + l, src);
+        n_seg += __popc(dirty);
+        dirty = 0;
+
+        // ---- jump to the next step at which some lane runs empty
+        const int32_t m = __reduce_min_sync(gmask, left);
+        if (m <= 0 || m >= n_steps - i) break;
+        src += m;
+        left -= m;
+        i += m;
+    }
+
+    rec[n_rec + l] = make_int2(-1, from == -1 ? l : from); // the eight terminators (:982-999)
+    if (!tail_stored) tail = row; // the reference leaves final_2 unwritten here; store the intended rows
+    chunks[chunk].tail[l] = tail;
+    if (l == 0) {
+        CvrChunk* c = chunks + chunk;
+        c->start = s;
+        c->len = len;
+        c->first_row = (int32_t)r0;
+        c->last_row = (int32_t)r1;
+        c->split0 = split0;
+        c->split1 = split1;
+        c->n_rec = n_rec;
+        seg_count[chunk] = n_seg;
+    }
+  } // next chunk of this group
+}
+
 // One warp per chunk; thread `lane_id` owns CVR element 32k + lane_id of window k, i.e.
 // step 4k + (lane_id >> 3), SIMD lane (lane_id & 7).
 __global__ void __launch_bounds__(128)
@@ -412,6 +650,10 @@ cvr_collect_rows_kernel(const RdT* __restrict__ rd, int64_t n_rows,
 void cvr_preload_convert_kernels()
 {
     cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, cvr_schedule_group_kernel<int32_t>);
+    cudaFuncGetAttributes(&a, cvr_schedule_group_kernel<int64_t>);
+    cudaFuncGetAttributes(&a, cvr_row_bitmap_kernel<int32_t>);
+    cudaFuncGetAttributes(&a, cvr_row_bitmap_kernel<int64_t>);
     cudaFuncGetAttributes(&a, cvr_schedule_warp_kernel<int32_t>);
     cudaFuncGetAttributes(&a, cvr_schedule_warp_kernel<int64_t>);
     cudaFuncGetAttributes(&a, cvr_permute_kernel);
@@ -477,14 +719,32 @@ int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream)
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
-    const int64_t want = ((int64_t)a.n_chunks * 32 + threads - 1) / threads;
-    const int sched_blocks = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
-    if (a.rd64)
-        cvr_schedule_warp_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
-            a.rd64, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
-    else
-        cvr_schedule_warp_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
-            a.rd32, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+    int launched = 0;
+    const char* mode = getenv("CVR_SCHEDULE"); // "warp": the one-warp-per-chunk scheduler (A/B, tests)
+    if (a.row_bitmap && !(mode && strcmp(mode, "warp") == 0)) {
+        const unsigned bm_blocks = (unsigned)((a.n_rows + 2 + 63 + 255) / 256);
+        if (a.rd64) cvr_row_bitmap_kernel<int64_t><<<bm_blocks, 256, 0, stream>>>(a.rd64, a.n_rows, a.row_bitmap);
+        else cvr_row_bitmap_kernel<int32_t><<<bm_blocks, 256, 0, stream>>>(a.rd32, a.n_rows, a.row_bitmap);
+        const int64_t want = ((int64_t)a.n_chunks * 8 + threads - 1) / threads;
+        const int sched_blocks = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+        if (a.rd64)
+            cvr_schedule_group_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
+                a.rd64, a.row_bitmap, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+        else
+            cvr_schedule_group_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
+                a.rd32, a.row_bitmap, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+        launched = 2;
+    } else {
+        const int64_t want = ((int64_t)a.n_chunks * 32 + threads - 1) / threads;
+        const int sched_blocks = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+        if (a.rd64)
+            cvr_schedule_warp_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
+                a.rd64, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+        else
+            cvr_schedule_warp_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
+                a.rd32, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+        launched = 1;
+    }
     if (cudaGetLastError() != cudaSuccess) return -1;
     const int64_t warps = a.n_chunks;
     const int perm_blocks = (int)((warps * 32 + threads - 1) / threads);
@@ -492,7 +752,7 @@ int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream)
                                                             a.seg_count, a.csr_val, a.csr_col,
                                                             a.cvr_vals, a.cvr_cols);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    return 2;
+    return launched + 1;
 }
 
 // The reference's readMatrix leaves row_delim[k] = nnz-1 for every k after the last non-empty row

@@ -82,6 +82,7 @@ struct CvrConvertArgs {
     // scratch
     int2* segments;    // (pos, src) entries, CVR_SEG_STRIDE*T + n_rows + slack
     int32_t* seg_count;
+    uint32_t* row_bitmap; // (n_rows + 2) / 32 + 2 words: bit r = row r is not empty (NULL: warp scheduler)
 };
 
 // Rows that are ACCUMULATED (atomics) rather than stored once: chunk first rows that end while

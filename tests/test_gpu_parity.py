@@ -104,6 +104,22 @@ def test_generated_matrices_vs_oracle_port(cvr, name):
             assert_y_close(y1, csr, np.ones(csr.n_cols + 1), f"{name} T={T} x=1")
 
 
+def test_warp_per_chunk_scheduler_still_bit_exact(cvr, monkeypatch):
+    """CVR_SCHEDULE=warp selects the one-warp-per-chunk lane scheduler (round 1); the default schedules a chunk
+    with 8 threads.  Both must emit the reference's structure bit for bit."""
+    from cvr_b200 import gen
+    monkeypatch.setenv("CVR_SCHEDULE", "warp")
+    for name in ("long", "road", "rmat"):
+        make, Ts = GENERATED[name]
+        d = make(gen)
+        csr = to_oracle_csr(d)
+        for T in Ts:
+            T = min(T, csr.nnz // 16)
+            with cvr.CvrMatrix(d.to_host(), T) as m:
+                assert m.info["kernel_launches"] == 5  # no row bitmap kernel
+                assert_structure_equal(m.export(), oracle.convert(csr, T, "port", fill_missing_tail=True), f"{name} T={T}")
+
+
 def test_maximum_chunk_count_and_single_chunk(cvr):
     from cvr_b200 import gen
     d = gen.random_sparse(500, 700, 4000, seed=46, empty_frac=0.1)
@@ -127,7 +143,7 @@ def test_auto_chunks_and_device_csr_entry(cvr):
     with cvr.CvrMatrix(d, 0) as m:  # n_chunks = 0: cvr_auto_chunks, CSR already on the device
         info = m.info
         assert info["n_chunks"] % torch.cuda.get_device_properties(0).multi_processor_count == 0
-        assert info["kernel_launches"] == 5  # schedule, permute, mark, 2 x collect
+        assert info["kernel_launches"] == 6  # row bitmap, schedule, permute, mark, 2 x collect
         want = oracle.convert(csr, info["n_chunks"], "port", fill_missing_tail=True)
         assert_structure_equal(m.export(), want, "auto")
         y, _ = m.spmv(x)
