@@ -294,6 +294,12 @@ __device__ __forceinline__ int nth_set_bit(uint32_t w, int n) // position of the
     return pos;
 }
 
+// position of the n-th (0-based) set bit of an 8-bit lane mask, 8 if it has at most n set bits
+__device__ __forceinline__ int nth_or_8(unsigned m, int n)
+{
+    return __popc(m) > n ? nth_set_bit(m, n) : 8;
+}
+
 // bit r of the bitmap: row r holds at least one element (rows 0 .. n_rows+1; the array has one spare word)
 template <typename RdT>
 __global__ void cvr_row_bitmap_kernel(const RdT* __restrict__ rd, int64_t n_rows, uint32_t* __restrict__ bitmap)
@@ -308,13 +314,12 @@ template <typename RdT>
 __global__ void __launch_bounds__(128)
 cvr_schedule_group_kernel(const RdT* __restrict__ rd, const uint32_t* __restrict__ bitmap, int64_t nnz,
                           int64_t n_rows, int32_t T, int32_t* __restrict__ record, CvrChunk* __restrict__ chunks,
-                          int2* __restrict__ segments, int32_t* __restrict__ seg_count)
+                          int2* __restrict__ segments, int32_t* __restrict__ seg_count, int32_t* __restrict__ next_chunk)
 {
     const int l = threadIdx.x & 7;                    // my SIMD lane
     const int gshift = threadIdx.x & 24;              // first lane of my group inside the warp
     const unsigned gmask = 0xffu << gshift;           // member mask of my group
     const unsigned lt = (1u << l) - 1u;               // SIMD lanes before mine
-    const int32_t n_groups = (gridDim.x * blockDim.x) >> 3;
     auto gballot = [&](bool p) { return (__ballot_sync(gmask, p) >> gshift) & 0xffu; };
     // rows r .. r+31 of the bitmap as one word (bit j: row r + j is not empty)
     auto window = [&](int64_t r) {
@@ -324,16 +329,26 @@ cvr_schedule_group_kernel(const RdT* __restrict__ rd, const uint32_t* __restrict
     const int64_t per = (nnz / T / 16) * 16;
     const int64_t brk = (nnz - per * T) / 16;
 
-  for (int32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; chunk < T; chunk += n_groups) {
+  // Work distribution: every group fetches its next chunk from a global counter.  Chunks differ wildly in cost
+  // (a chunk inside one hub row is a handful of steals, a chunk of 4096 one-element rows is 4096 feeds), so a
+  // static round robin leaves most warps idle at the end (23 % warps active on R-MAT-24,
+  // profiles/r02_prof_schedule_group_rmat24_summary.txt).  The four groups of a warp are NOT forced into
+  // lockstep: a warp-synchronous event loop was measured (road 1.32 -> 1.39 ms, R-MAT-24 unchanged) and dropped.
+  for (;;) {
+    int32_t chunk = 0;
+    if (l == 0) chunk = atomicAdd(next_chunk, 1);
+    chunk = __shfl_sync(gmask, chunk, gshift);
+    if (chunk >= T) break;
+    const int64_t c = chunk;
     int64_t s, e; // nnz-balanced slice of this chunk, multiples of 16 (spmv.cpp:584-586, :615-627)
-    if (chunk < brk) {
-        s = chunk * (per + 16);
-        e = (chunk + 1) * (per + 16);
+    if (c < brk) {
+        s = c * (per + 16);
+        e = (c + 1) * (per + 16);
     } else {
-        s = chunk * per + brk * 16;
-        e = (chunk + 1) * per + brk * 16;
+        s = c * per + brk * 16;
+        e = (c + 1) * per + brk * 16;
     }
-    if (chunk == T - 1) e = nnz;
+    if (c == T - 1) e = nnz;
     const int64_t r0 = last_row_not_after(rd, 0, n_rows, s);        // :631-650
     int64_t r1 = last_row_not_after(rd, r0, n_rows, e - 1);         // :652-667
     while (r1 <= n_rows && rd[r1 + 1] == rd[r1]) r1++;              // :687-688 (degenerate tails only)
@@ -341,8 +356,8 @@ cvr_schedule_group_kernel(const RdT* __restrict__ rd, const uint32_t* __restrict
     const int32_t len = (int32_t)(e - s);
     const int32_t n_steps = len / CVR_W;
 
-    int2* rec = reinterpret_cast<int2*>(record + cvr_record_offset(chunk, r0));
-    int2* seg = segments + cvr_segment_offset(chunk, r0);
+    int2* rec = reinterpret_cast<int2*>(record + cvr_record_offset(c, r0));
+    int2* seg = segments + cvr_segment_offset(c, r0);
     int32_t n_rec = 0, n_seg = 0;
 
     // lane trackers (vPack_valID / rowID / count / flag, :711-759): lane l starts on row r0 + l, empty or not
@@ -366,20 +381,48 @@ cvr_schedule_group_kernel(const RdT* __restrict__ rd, const uint32_t* __restrict
     int32_t split0 = 0, split1 = 0, tail = 0;
 
     int32_t i = 0;
-    while (i < n_steps) {
+    bool active = n_steps > 0;
+    while (active) {
+      {
         unsigned zero_mask = gballot(left == 0);
         if (zero_mask && next_row < r1) {
-            // ---- fast path: feed ALL lanes that ran empty at this step in one pass: in lane order they take
-            // the next non-empty rows, i.e. the j-th empty lane gets the j-th set bit of the window.  Only rows
-            // strictly before r1 qualify (feeding r1 snapshots the tail, :844-857) and all of them must lie
-            // inside the 32-row window; otherwise the one-lane path below handles the step.
-            unsigned w = window(next_row);
-            if (r1 - next_row < 32) w &= (1u << (int)(r1 - next_row)) - 1u;
+            // ---- fast path: feed the lanes that ran empty at this step in one pass: in lane order they take
+            // the next non-empty rows, i.e. the j-th empty lane gets the j-th set bit of the row bitmap from
+            // next_row on.  The bitmap is read 32 rows at a time and the pass simply moves on to the next
+            // window until every lane is served (sparse regions of R-MAT hold a few non-empty rows per window)
+            // or row r1 is reached: only rows strictly before r1 qualify (feeding r1 snapshots the tail,
+            // :844-857); lanes still unserved then go through the one-lane path below, which preserves the
+            // lane order because the served ones are the lowest-ranked.
+            const int rank = __popc(zero_mask & lt);       // my position among the empty lanes
             const int k = __popc(zero_mask);
-            if (__popc(w) >= k) {
-                const bool mine = (zero_mask >> l) & 1u;
-                const int bit = mine ? nth_set_bit(w, __popc(zero_mask & lt)) : 0;
-                const int64_t new_row = next_row + bit;
+            int served = 0;                                 // empty lanes served so far (group-uniform)
+            int64_t new_row = 0, last_taken = next_row - 1;
+            {
+                unsigned w = window(next_row);              // the common case: everything inside one window
+                if (r1 - next_row < 32) w &= (1u << (int)(r1 - next_row)) - 1u;
+                if (__popc(w) >= k) {
+                    new_row = next_row + nth_set_bit(w, rank);
+                    last_taken = next_row + nth_set_bit(w, k - 1);
+                    served = k;
+                } else {
+                    int64_t base = next_row;
+                    while (served < k && base < r1) {
+                        if (base != next_row) {
+                            w = window(base);
+                            if (r1 - base < 32) w &= (1u << (int)(r1 - base)) - 1u;
+                        }
+                        const int c = __popc(w);
+                        const int take = min(c, k - served);
+                        if (rank >= served && rank < served + take) new_row = base + nth_set_bit(w, rank - served);
+                        if (take > 0) last_taken = base + nth_set_bit(w, take - 1);
+                        served += take;
+                        base += 32;
+                    }
+                }
+            }
+            if (served > 0) {
+                const unsigned served_mask = zero_mask & ~(0xffu << nth_or_8(zero_mask, served)); // lowest `served` bits
+                const bool mine = (served_mask >> l) & 1u;
                 int64_t a0 = 0, a1 = 0;
                 if (mine) {
                     a0 = (int64_t)rd[new_row];
@@ -387,7 +430,7 @@ cvr_schedule_group_kernel(const RdT* __restrict__ rd, const uint32_t* __restrict
                 }
                 const unsigned first_mask = gballot(mine && row == (int32_t)r0); // <= 1 lane
                 if (first_mask) split0 = i * CVR_W + (__ffs(first_mask) - 1);    // :826-829
-                const unsigned rec_mask = zero_mask & ~first_mask;
+                const unsigned rec_mask = served_mask & ~first_mask;
                 if (mine && !((first_mask >> l) & 1u))
                     rec[n_rec + __popc(rec_mask & lt)] = make_int2(i * CVR_W + l, row); // :832-834
                 n_rec += __popc(rec_mask);
@@ -396,9 +439,9 @@ cvr_schedule_group_kernel(const RdT* __restrict__ rd, const uint32_t* __restrict
                     row = (int32_t)new_row;
                     left = (int32_t)(a1 - a0);
                 }
-                next_row += nth_set_bit(w, k - 1) + 1;
-                dirty |= zero_mask;
-                zero_mask = 0;
+                next_row = last_taken + 1;
+                dirty |= served_mask;
+                zero_mask &= ~served_mask;
             }
         }
         while (zero_mask) {
@@ -477,10 +520,14 @@ cvr_schedule_group_kernel(const RdT* __restrict__ rd, const uint32_t* __restrict
 
         // ---- jump to the next step at which some lane runs empty
         const int32_t m = __reduce_min_sync(gmask, left);
-        if (m <= 0 || m >= n_steps - i) break;
-        src += m;
-        left -= m;
-        i += m;
+        if (m <= 0 || m >= n_steps - i) {
+            active = false; // no further event inside this chunk
+        } else {
+            src += m;
+            left -= m;
+            i += m;
+        }
+      }
     }
 
     rec[n_rec + l] = make_int2(-1, from == -1 ? l : from); // the eight terminators (:982-999)
@@ -498,6 +545,7 @@ cvr_schedule_group_kernel(const RdT* __restrict__ rd, const uint32_t* __restrict
         seg_count[chunk] = n_seg;
     }
   } // next chunk of this group
+
 }
 
 // One warp per chunk; thread `lane_id` owns CVR element 32k + lane_id of window k, i.e.
@@ -727,12 +775,16 @@ int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream)
         else cvr_row_bitmap_kernel<int32_t><<<bm_blocks, 256, 0, stream>>>(a.rd32, a.n_rows, a.row_bitmap);
         const int64_t want = ((int64_t)a.n_chunks * 8 + threads - 1) / threads;
         const int sched_blocks = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+        int32_t* next_chunk = a.seg_count + a.n_chunks; // one spare int behind the per-chunk counts
+        if (cudaMemsetAsync(next_chunk, 0, sizeof(int32_t), stream) != cudaSuccess) return -1;
         if (a.rd64)
             cvr_schedule_group_kernel<int64_t><<<sched_blocks, threads, 0, stream>>>(
-                a.rd64, a.row_bitmap, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+                a.rd64, a.row_bitmap, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count,
+                next_chunk);
         else
             cvr_schedule_group_kernel<int32_t><<<sched_blocks, threads, 0, stream>>>(
-                a.rd32, a.row_bitmap, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count);
+                a.rd32, a.row_bitmap, a.nnz, a.n_rows, a.n_chunks, a.record, a.chunks, a.segments, a.seg_count,
+                next_chunk);
         launched = 2;
     } else {
         const int64_t want = ((int64_t)a.n_chunks * 32 + threads - 1) / threads;
