@@ -469,6 +469,22 @@ __global__ void cvr_clear_rows_kernel(double* __restrict__ y, const int32_t* __r
     }
 }
 
+// When a large share of the rows has to be cleared (R-MAT-24: 6.7 M empty rows of 16.7 M) one streaming pass
+// over all of y beats millions of scattered 8-byte stores (60 us -> 25 us per sweep): 16-byte stores,
+// grid-stride; same programmatic-launch role as cvr_clear_rows_kernel.
+__global__ void cvr_zero_y_kernel(double* __restrict__ y, int64_t n)
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    // y comes from cudaMalloc or a tensor: 16-byte aligned in practice, but do not rely on it
+    const int64_t head = (reinterpret_cast<uintptr_t>(y) & 8) ? 1 : 0;
+    if (tid == 0 && head) y[0] = 0.0;
+    double2* y2 = reinterpret_cast<double2*>(y + head);
+    const int64_t n2 = (n - head) / 2;
+    for (int64_t i = tid; i < n2; i += stride) y2[i] = make_double2(0.0, 0.0);
+    if (tid == 0 && ((n - head) & 1)) y[n - 1] = 0.0;
+}
+
 // All-to-all flag barrier over peer-mapped memory, run by the first n_ranks threads of one block:
 // every rank writes `epoch` into its slot of every rank's flag array (after a system-scope fence,
 // so the rows it published are visible first) and waits until all of its own slots carry the epoch.
@@ -705,6 +721,11 @@ int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const
     bool after_clear_kernel = false;
     if (y_is_clear) {
         // the previous iteration's epilogue kernel already cleared the accumulated rows
+    } else if (rows.boundary && !publish && (int64_t)n_clear * 4 > n_rows) {
+        // more than a quarter of the rows would be cleared one by one: zero all of y instead
+        cvr_zero_y_kernel<<<sms * 8, 256, 0, stream>>>(y, n_rows + 1);
+        launched++;
+        after_clear_kernel = true;
     } else if (rows.boundary) {
         const int cb = (n_clear + 255) / 256;
         const int cap = sms * 8;
@@ -808,6 +829,7 @@ void cvr_preload_spmv_kernels()
         CVR_FOR_VARIANT(v, P::preload())
     }
     cudaFuncGetAttributes(&a, cvr_clear_rows_kernel);
+    cudaFuncGetAttributes(&a, cvr_zero_y_kernel);
     // The multi-GPU kernels wait for each other on the device (flag barrier).  CUDA loads a kernel lazily at
     // its first launch and that load can synchronise with running work: a first launch issued while a peer's
     // epilogue is already spinning at the barrier would never get through.  Load everything up front.
