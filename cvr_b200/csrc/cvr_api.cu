@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 thread_local char g_cvr_err[512] = "";
@@ -922,8 +923,10 @@ int cvr_save(cvr_handle_t* h, const char* path)
 {
     if (!h || !path) return fail(CVR_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    FILE* f = fopen(path, "wb");
-    if (!f) return fail(CVR_ERR_INVALID, "cannot open %s for writing", path);
+    // written next to the target and renamed when complete: a failed save never leaves a partial file there
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(CVR_ERR_INVALID, "cannot open %s for writing", tmp.c_str());
     CvrFileHeader hd{};
     memcpy(hd.magic, CVR_FILE_MAGIC, 8);
     hd.n_rows = h->n_rows;
@@ -943,7 +946,9 @@ int cvr_save(cvr_handle_t* h, const char* path)
     if (rc == CVR_OK) rc = copy_out(f, h->chunks, sizeof(CvrChunk) * (size_t)h->n_chunks, buf);
     if (rc == CVR_OK) rc = copy_out(f, h->rows.boundary, sizeof(int32_t) * (size_t)h->rows.n_boundary, buf);
     if (rc == CVR_OK) rc = copy_out(f, h->rows.empty, sizeof(int32_t) * (size_t)h->rows.n_empty, buf);
-    if (fclose(f) != 0 && rc == CVR_OK) rc = fail(CVR_ERR_INVALID, "close failed on %s", path);
+    if (fclose(f) != 0 && rc == CVR_OK) rc = fail(CVR_ERR_INVALID, "close failed on %s", tmp.c_str());
+    if (rc == CVR_OK && rename(tmp.c_str(), path) != 0) rc = fail(CVR_ERR_INVALID, "cannot rename %s to %s", tmp.c_str(), path);
+    if (rc != CVR_OK) remove(tmp.c_str());
     return rc;
 }
 
@@ -958,10 +963,28 @@ int cvr_load(const char* path, int device, cvr_handle_t** out)
     const double t0 = wall_seconds();
     CvrFileHeader hd{};
     if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, CVR_FILE_MAGIC, 8) != 0 ||
-        hd.chunk_bytes != (int32_t)sizeof(CvrChunk) || hd.nnz < 16 || hd.nnz % 16 || hd.n_chunks < 1 ||
-        hd.record_ints != cvr_record_ints(hd.n_rows, hd.n_chunks)) {
+        hd.chunk_bytes != (int32_t)sizeof(CvrChunk)) {
         fclose(f);
         return fail(CVR_ERR_INVALID, "%s is not a CVR file of this library version", path);
+    }
+    // the header is not trusted: every count is range-checked and the file must have exactly the size they imply
+    const bool sane = hd.n_rows >= 1 && hd.n_rows <= 0x7ffffff0LL && hd.n_cols >= 1 && hd.n_cols <= 0x7ffffff0LL &&
+                      hd.nnz >= 16 && hd.nnz % 16 == 0 && hd.n_chunks >= 1 && (int64_t)hd.n_chunks <= hd.nnz / 16 &&
+                      hd.record_ints == cvr_record_ints(hd.n_rows, hd.n_chunks) && hd.n_boundary >= 0 &&
+                      hd.n_boundary <= 9 * (int64_t)hd.n_chunks && hd.n_empty >= 0 && hd.n_empty <= hd.n_rows + 1 &&
+                      hd.n_records >= 8 * (int64_t)hd.n_chunks && 2 * hd.n_records <= hd.record_ints;
+    int64_t expect = (int64_t)sizeof(hd);
+    if (sane)
+        expect += 12 * hd.nnz + 4 * hd.record_ints + (int64_t)sizeof(CvrChunk) * hd.n_chunks +
+                  4 * ((int64_t)hd.n_boundary + hd.n_empty);
+    bool size_ok = false;
+    if (sane && fseek(f, 0, SEEK_END) == 0) {
+        size_ok = (int64_t)ftell(f) == expect;
+        fseek(f, (long)sizeof(hd), SEEK_SET);
+    }
+    if (!sane || !size_ok) {
+        fclose(f);
+        return fail(CVR_ERR_INVALID, "%s: inconsistent CVR file header (counts out of range or wrong file size)", path);
     }
     cvr_handle* h = new (std::nothrow) cvr_handle();
     if (!h) {
@@ -1015,6 +1038,28 @@ int cvr_load(const char* path, int device, cvr_handle_t** out)
                    cudaMemcpyDeviceToHost) != cudaSuccess) {
         delete h;
         return fail(CVR_ERR_CUDA, "descriptor copy failed");
+    }
+    // chunk descriptors: contiguous nnz slices in multiples of 16, rows in range and non-decreasing, record
+    // regions inside the record array -- the kernels index with these without further checks
+    {
+        int64_t at = 0, n_records = 0;
+        int32_t prev_row = 0;
+        bool ok = true;
+        for (int32_t t = 0; t < h->n_chunks && ok; t++) {
+            const CvrChunk& c = h->host_chunks[(size_t)t];
+            ok = c.start == at && c.len >= 16 && c.len % 16 == 0 && c.first_row >= prev_row && c.last_row >= c.first_row &&
+                 c.last_row <= h->n_rows && c.n_rec >= 0 && c.split0 >= 0 && c.split0 < c.len && c.split1 >= -1 &&
+                 c.split1 < c.len &&
+                 cvr_record_offset(t, c.first_row) + 2 * ((int64_t)c.n_rec + CVR_W) <= h->record_ints;
+            for (int q = 0; q < CVR_W && ok; q++) ok = c.tail[q] >= 0 && c.tail[q] <= h->n_rows;
+            at += c.len;
+            n_records += c.n_rec + CVR_W;
+            prev_row = c.first_row;
+        }
+        if (!ok || at != h->nnz || n_records != h->n_records) {
+            delete h;
+            return fail(CVR_ERR_INVALID, "%s: chunk descriptors are inconsistent with the header", path);
+        }
     }
     h->create_seconds = wall_seconds() - t0;
     *out = h;

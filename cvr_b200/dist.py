@@ -186,6 +186,7 @@ class PeerPublisher:
         buffer only holds the entries it reads (plus its own rows), so the full vector is assembled
         from the owners' slices -- one broadcast per rank, outside the iteration loop."""
         torch.cuda.synchronize(self.dev)
+        self.m.check_async_error()  # a flag barrier that timed out means stale x: raise instead of returning it
         mine = self.x_tensor()
         out = torch.zeros_like(mine)
         for r in range(self.world):

@@ -219,10 +219,34 @@ def test_save_load_round_trip(cvr, tmp_path):
         yb, _ = m2.spmv(x)
         assert_y_close(yb, csr, x, "reloaded")
         assert np.array_equal(ya[np.abs(ya) > 0] != 0, yb[np.abs(ya) > 0] != 0)
-    with open(p, "r+b") as f:
-        f.write(b"XXXX")
-    with pytest.raises(cvr.CvrError):
-        cvr.CvrMatrix.load(p)
+    assert not os.path.exists(p + ".tmp")  # written under a temporary name, renamed when complete
+    good = open(p, "rb").read()
+    # the loader does not trust the file: wrong magic, truncation, padding, counts and descriptors out of range
+    import struct
+    hdr = struct.Struct("<8s5q4i")
+    fields = list(hdr.unpack_from(good))
+
+    def rewritten(**kw):
+        f = list(fields)
+        names = ["magic", "n_rows", "n_cols", "nnz", "record_ints", "n_records", "n_chunks", "n_boundary", "n_empty", "chunk_bytes"]
+        for k, v in kw.items():
+            f[names.index(k)] = v
+        return hdr.pack(*f) + good[hdr.size:]
+
+    chunk0 = hdr.size + 12 * fields[3] + 4 * fields[4]  # first chunk descriptor: start (i64), len, first_row, ...
+    bad_desc = bytearray(good)
+    struct.pack_into("<i", bad_desc, chunk0 + 12, 10 ** 9)  # first_row far beyond n_rows
+    for what, blob in (("magic", b"XXXX" + good[4:]), ("truncated", good[:-8]), ("padded", good + b"\0" * 16),
+                       ("n_rows", rewritten(n_rows=-5)), ("n_chunks", rewritten(n_chunks=fields[6] + 1)),
+                       ("n_empty", rewritten(n_empty=2 ** 30)), ("descriptor", bytes(bad_desc))):
+        with open(p, "wb") as f:
+            f.write(blob)
+        with pytest.raises(cvr.CvrError):
+            cvr.CvrMatrix.load(p)
+    with open(p, "wb") as f:
+        f.write(good)
+    with cvr.CvrMatrix.load(p) as m3:
+        assert m3.n_chunks == 200
 
 
 def test_64bit_row_delimiters_entry(cvr):
