@@ -88,7 +88,8 @@ struct cvr_handle {
     int64_t device_bytes = 0;
     std::vector<CvrChunk> host_chunks; // copy of the descriptors (export / info)
     // optional per-launch timing of the SpMV kernel alone (cvr_set_kernel_timing)
-    unsigned int* done_counter = nullptr; // [0] last-block detection of the publish epilogue,
+    unsigned int* done_counter = nullptr; // [2], [3]: next-chunk / warps-finished counters of the sweep's dynamic chunk queue;
+                                          // [0] last-block detection of the publish epilogue,
                                           // [1] epoch of the first peer barrier that timed out (0 = none)
     // CUDA graph of GRAPH_UNROLL iterations of the host-facing loop (cvr_spmv with iters >> 1): captured once
     cudaStream_t copy_stream = nullptr;          // D2H of finished row slabs behind the sweep (cvr_spmv, iters = 1)
@@ -195,8 +196,8 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
     CUDA_TRY(dev_alloc(h, &h->y, (size_t)h->n_rows + 1));
     // counters of the multi-GPU epilogue: allocated here, not lazily inside the iteration loop (an allocation
     // or memset issued while a peer already spins at the flag barrier may have to wait for it)
-    CUDA_TRY(dev_alloc(h, &h->done_counter, 2));
-    CUDA_TRY(cudaMemsetAsync(h->done_counter, 0, 2 * sizeof(unsigned int), h->stream));
+    CUDA_TRY(dev_alloc(h, &h->done_counter, 4));
+    CUDA_TRY(cudaMemsetAsync(h->done_counter, 0, 4 * sizeof(unsigned int), h->stream));
 
     int2* segments = nullptr;
     int32_t* seg_count = nullptr;
@@ -504,6 +505,15 @@ int cvr_create_from_device(const cvr_csr_t* csr_dev, int32_t n_chunks, int devic
 static int spmv_device_impl(cvr_handle_t* h, const double* x_dev, double* y_dev, const CvrPublish* pub,
                             void* cuda_stream, const CvrBarrier* bar = nullptr, bool y_is_clear = false);
 
+// the sweep's dynamic chunk queue (two counters behind done_counter); CVR_DYNAMIC_CHUNKS=0 keeps the static
+// round robin.  Read per call so that tools/kernel_ab.py can switch it at run time.
+static unsigned int* chunk_queue(cvr_handle_t* h)
+{
+    const char* e = getenv("CVR_DYNAMIC_CHUNKS");
+    if (e && *e == '0') return nullptr;
+    return h->done_counter ? h->done_counter + 2 : nullptr;
+}
+
 int cvr_spmv_device(cvr_handle_t* h, const double* x_dev, double* y_dev, void* cuda_stream)
 {
     return spmv_device_impl(h, x_dev, y_dev, nullptr, cuda_stream);
@@ -527,8 +537,8 @@ int cvr_spmv_publish(cvr_handle_t* h, const double* x_dev, double* y_dev, const 
     b.timeout_cycles = barrier_timeout_cycles(h->device);
     if (!h->done_counter) {
         CUDA_TRY(cudaSetDevice(h->device));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->done_counter), 2 * sizeof(unsigned int)));
-        CUDA_TRY(cudaMemset(h->done_counter, 0, 2 * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->done_counter), 4 * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(h->done_counter, 0, 4 * sizeof(unsigned int)));
     }
     b.error = h->done_counter + 1;
     if (pub->n_dst < 1 || pub->n_dst > CVR_MAX_PEERS)
@@ -571,7 +581,7 @@ static int spmv_device_impl(cvr_handle_t* h, const double* x_dev, double* y_dev,
     const int launched = cvr_launch_spmv(h->variant, h->chunks, h->n_chunks, h->vals, h->cols, h->record,
                                          x_dev, y_dev, h->n_rows, h->rows, pub,
                                          static_cast<cudaStream_t>(cuda_stream), eb, ee, bar,
-                                         h->done_counter, y_is_clear);
+                                         h->done_counter, y_is_clear, 0, -1, chunk_queue(h));
     if (launched < 0)
         return fail(CVR_ERR_CUDA, "SpMV launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += launched;
@@ -613,7 +623,7 @@ int cvr_spmv(cvr_handle_t* h, const double* x_host, double* y_host, int32_t iter
                 const int32_t c1 = (int32_t)((int64_t)h->n_chunks * (k + 1) / SLABS);
                 const int launched = cvr_launch_spmv(h->variant, h->chunks, h->n_chunks, h->vals, h->cols, h->record, h->x,
                                                      h->y, h->n_rows, h->rows, nullptr, h->stream, nullptr, nullptr,
-                                                     nullptr, nullptr, /*y_is_clear=*/k > 0, c0, c1);
+                                                     nullptr, nullptr, /*y_is_clear=*/k > 0, c0, c1, chunk_queue(h));
                 if (launched < 0)
                     return fail(CVR_ERR_CUDA, "SpMV launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 h->launches += launched;
@@ -1014,8 +1024,8 @@ int cvr_load(const char* path, int device, cvr_handle_t** out)
         if ((e = dev_alloc(h, &h->rows.empty, (size_t)hd.n_empty + 1)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->x, (size_t)h->n_cols + 1)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->y, (size_t)h->n_rows + 1)) != cudaSuccess) break;
-        if ((e = dev_alloc(h, &h->done_counter, 2)) != cudaSuccess) break;
-        if ((e = cudaMemset(h->done_counter, 0, 2 * sizeof(unsigned int))) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->done_counter, 4)) != cudaSuccess) break;
+        if ((e = cudaMemset(h->done_counter, 0, 4 * sizeof(unsigned int))) != cudaSuccess) break;
     } while (0);
     if (e != cudaSuccess) {
         fclose(f);

@@ -102,13 +102,16 @@ int cvr_launch_convert(const CvrConvertArgs& a, cudaStream_t stream);
 // repairs the reference's off-by-one trailing delimiters (nnz-1 -> nnz) in a DEVICE delimiter array we own
 int cvr_launch_fix_last_delim(int32_t* rd32, int64_t* rd64, int64_t n_rows, int64_t nnz, cudaStream_t stream);
 // ev_begin / ev_end (optional) bracket the SpMV kernel alone, after y has been cleared;
-// [chunk_begin, chunk_end) restricts the sweep to a slab of chunks (chunk_end < 0: through the last chunk)
+// [chunk_begin, chunk_end) restricts the sweep to a slab of chunks (chunk_end < 0: through the last chunk);
+// chunk_queue (optional): two zero-initialised device words -- chunks beyond each warp's first are then handed
+// out in index order from an atomic counter (the sweep resets both words itself when its last warp finishes)
 int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const double* vals,
                     const int32_t* cols, const int32_t* record, const double* x, double* y,
                     int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
                     cudaStream_t stream, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr,
                     const CvrBarrier* barrier = nullptr, unsigned int* done_counter = nullptr,
-                    bool y_is_clear = false, int32_t chunk_begin = 0, int32_t chunk_end = -1);
+                    bool y_is_clear = false, int32_t chunk_begin = 0, int32_t chunk_end = -1,
+                    unsigned int* chunk_queue = nullptr);
 int cvr_launch_peer_barrier(const CvrBarrier& b, cudaStream_t stream);
 // used[c] = 1 for every column id that occurs in cols[0..nnz)
 // chunk_any[t] = OR of needs[first_row..last_row] of chunk t
@@ -120,7 +123,7 @@ int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used,
 int cvr_pick_sweep_variant(int64_t nnz, int64_t n_rows);
 // resident warps per SM of that geometry (sizes the automatic chunk count)
 int cvr_spmv_resident_warps_per_sm(int variant);
-// its name ("tile7x7", "tile11x5", ...)
+// its name ("tile7x6", "tile11x5", ...)
 const char* cvr_spmv_kernel_name(int variant);
 
 // force-load the kernels' module so the first timed call does not pay CUDA's lazy loading

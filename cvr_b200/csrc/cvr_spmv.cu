@@ -6,7 +6,7 @@
 // reference kernel mishandles.
 //
 // One sweep kernel, cvr_spmv_tile_kernel<TB, NB, kPublish>, in two geometries picked per matrix (see
-// cvr_pick_sweep_variant): TB = 7 steps per walker at 7 resident blocks per SM for short-row matrices,
+// cvr_pick_sweep_variant): TB = 7 steps per walker at 6 resident blocks per SM for short-row matrices,
 // TB = 11 at 5 blocks for long regular rows; <..., kPublish> additionally pushes finished rows to peer
 // GPUs for the iterated multi-GPU SpMV.  What was measured against it on B200 in round 2 and removed
 // again (never faster on any BASELINE workload; numbers under profiles/, code in the git history):
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(WARPS * 32, NB)
 cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, int32_t T,
                      const double* __restrict__ vals, const int32_t* __restrict__ cols,
                      const int32_t* __restrict__ record, const double* __restrict__ x,
-                     double* __restrict__ y, const __grid_constant__ CvrPublish pub)
+                     double* __restrict__ y, const __grid_constant__ CvrPublish pub, unsigned int* queue)
 {
     using G = Geo<TB>;
     constexpr int TILE = G::TILE, QUARTER = G::QUARTER, FLAG_WORDS = G::FLAG_WORDS;
@@ -246,8 +246,14 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
     for (int k = 0; k < FLAG_WORDS; k++) s_flags[w][k][t] = 0u;
     __syncwarp();
 
-    // chunks [chunk_begin, T) of the matrix (the whole matrix unless the host pipelines the sweep in slabs)
-    for (int32_t chunk = chunk_begin + warp0; chunk < T; chunk += n_warps) {
+    // chunks [chunk_begin, T) of the matrix (the whole matrix unless the host pipelines the sweep in slabs).
+    // A warp's first chunk is its own index; further chunks come in index order from an atomic counter when the
+    // host passes a queue (requested at the start of a chunk, consumed at its end: the round trip is hidden),
+    // otherwise by static round robin.  Chunks are nnz-balanced but not record-balanced: with the static order
+    // the warps of R-MAT-24 finish up to 8 % apart (sm__warps_active 40.1 % of a possible 43.75 %).
+    for (int32_t chunk = chunk_begin + warp0; chunk < T;) {
+        int32_t next_chunk = chunk + n_warps;
+        if (queue && t == 0) next_chunk = chunk_begin + n_warps + (int32_t)atomicAdd(queue, 1u);
         const CvrChunk* cp = chunks + chunk;
         const int64_t start = cp->start;
         const int32_t len = cp->len;
@@ -446,6 +452,14 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
         }
         if (kPublish && publishing && pushed_upto <= chunk_last_row)
             publish_rows(cx, pushed_upto, chunk_last_row, t); // what the watermark had not reached
+        chunk = queue ? __shfl_sync(FULL, next_chunk, 0) : next_chunk;
+    }
+    // the last warp to leave resets the queue for the next launch (every warp has drawn its last ticket by then)
+    if (queue && t == 0) {
+        if (atomicAdd(queue + 1, 1u) == (unsigned)n_warps - 1u) {
+            queue[0] = 0u;
+            queue[1] = 0u;
+        }
     }
 }
 
@@ -569,24 +583,28 @@ __global__ void cvr_peer_barrier_kernel(const __grid_constant__ CvrBarrier b)
 }
 
 // ---- sweep geometries: cvr_spmv_tile_kernel<TB, NB>, TB steps per walker (tile = 32 TB elements), NB
-// resident blocks (4 warps each) per SM requested through __launch_bounds__.  Measured on B200
-// (profiles/r02_kernel_ab_tile_geometries.jsonl, kernel us): FEM 70.3 / 65.3 / 62.9, R-MAT-24 1358 / 1387 /
-// 1369, web 38.3 / 40.3 / 41.3, road 342.8 / 354.6 / 370.9 for 7x7 / 9x6 / 11x5 -- short rows want more
-// warps, long regular rows want the larger tile (fewer per-tile flag/carry operations per element).
+// resident blocks (4 warps each) per SM requested through __launch_bounds__.  Measured on B200 (kernel us):
+//   profiles/r02_kernel_ab_tile_geometries.jsonl   FEM 70.3 / 65.3 / 62.9, R-MAT-24 1358 / 1387 / 1369, web 38.3 / 40.3 /
+//   41.3, road 342.8 / 354.6 / 370.9 for 7x7 / 9x6 / 11x5 -- short rows want more warps, long regular rows the
+//   larger tile (fewer per-tile flag/carry operations per element);
+//   profiles/r02_kernel_ab_l1_capacity.txt   7x6 against 7x7: R-MAT-24 1316 / 1354, web 38.9 / 40.9, road 357 / 359
+//   -- six blocks need 99 KB of shared memory per SM, which leaves the x gather 156 KB of L1 instead of 124 KB,
+//   and 78 registers per thread instead of 72 with spills.  What the gather needs from L1 is room for the misses
+//   in flight: padding the blocks to 174 KB per SM (L1 60 KB) slows R-MAT-24 from 1390 to 2018 us.
 struct Variant {
     const char* name;
     int tb, nb;
 };
 constexpr Variant VARIANTS[] = {
-    {"tile7x7", 7, 7},
+    {"tile7x6", 7, 6},
     {"tile11x5", 11, 5},
-    {"tile9x6", 9, 6},
+    {"tile7x7", 7, 7},
 };
 constexpr int N_VARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
 
 int forced_variant()
 {
-    // CVR_SPMV_KERNEL = tile7x7 | tile11x5 | tile9x6 overrides the per-matrix choice; read per call so
+    // CVR_SPMV_KERNEL = tile7x6 | tile11x5 | tile7x7 overrides the per-matrix choice; read per call so
     // that tools/kernel_ab.py and the parity suite can switch it at run time
     const char* e = getenv("CVR_SPMV_KERNEL");
     if (!e || !*e) return -1;
@@ -626,13 +644,13 @@ struct TileOps {
     static cudaError_t launch(bool publish, int blocks, cudaStream_t stream, bool programmatic,
                               const CvrChunk* chunks, int32_t chunk_begin, int32_t chunk_end, const double* vals,
                               const int32_t* cols, const int32_t* record, const double* x, double* y,
-                              const CvrPublish& pub)
+                              const CvrPublish& pub, unsigned int* queue)
     {
         if (publish)
             return launch_ex(cvr_spmv_tile_kernel<TB, NB, true>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
-                             programmatic, chunks, chunk_begin, chunk_end, vals, cols, record, x, y, pub);
+                             programmatic, chunks, chunk_begin, chunk_end, vals, cols, record, x, y, pub, queue);
         return launch_ex(cvr_spmv_tile_kernel<TB, NB, false>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
-                         programmatic, chunks, chunk_begin, chunk_end, vals, cols, record, x, y, pub);
+                         programmatic, chunks, chunk_begin, chunk_end, vals, cols, record, x, y, pub, queue);
     }
     static void preload()
     {
@@ -644,9 +662,9 @@ struct TileOps {
 
 #define CVR_FOR_VARIANT(v, expr)                         \
     switch (v) {                                         \
-    case 0: { using P = TileOps<7, 7>; expr; } break;    \
+    case 0: { using P = TileOps<7, 6>; expr; } break;    \
     case 1: { using P = TileOps<11, 5>; expr; } break;   \
-    default: { using P = TileOps<9, 6>; expr; } break;   \
+    default: { using P = TileOps<7, 7>; expr; } break;   \
     }
 
 // resident blocks per SM of a variant on the current device (cached per device and variant)
@@ -710,7 +728,7 @@ int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const
                     int64_t n_rows, const CvrRowLists& rows, const CvrPublish* publish,
                     cudaStream_t stream, cudaEvent_t ev_begin, cudaEvent_t ev_end,
                     const CvrBarrier* barrier, unsigned int* done_counter, bool y_is_clear,
-                    int32_t chunk_begin, int32_t chunk_end)
+                    int32_t chunk_begin, int32_t chunk_end, unsigned int* chunk_queue)
 {
     if (chunk_end < 0) chunk_end = n_chunks;
     int launched = 0;
@@ -747,10 +765,13 @@ int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const
     // iteration on) the previous iteration's epilogue: launch as its programmatic dependent
     const bool pdl = pdl_enabled() && !(pub && (publish->mode & 8)); // mode bit 3: two shards share this device
     const bool programmatic = pdl && (after_clear_kernel || (pub && y_is_clear)) && !ev_begin;
+    // the chunk queue pays off when a warp walks many chunks (R-MAT-24, 16 per warp: 1399 -> 1354 us); with one
+    // or two chunks per warp the ticket only costs (web 38.9 -> 40.9 us)
+    if ((int64_t)(chunk_end - chunk_begin) < 4 * (int64_t)resident * WARPS) chunk_queue = nullptr;
     if (ev_begin) cudaEventRecord(ev_begin, stream);
     cudaError_t e = cudaSuccess;
     CVR_FOR_VARIANT(v, e = P::launch(pub, pblocks, stream, programmatic, chunks, chunk_begin, chunk_end, vals, cols,
-                                     record, x, y, pub ? *publish : none))
+                                     record, x, y, pub ? *publish : none, chunk_queue))
     if (e != cudaSuccess) return -1;
     launched++;
     if (ev_end) cudaEventRecord(ev_end, stream);
