@@ -37,6 +37,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE line, the JSON record: the process's fd 1 is pointed at stderr for the whole run
+# (NCCL prints its version banner to stdout on some boxes whatever NCCL_DEBUG_FILE says, torch warns, ...)
+# and the record is written to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_record(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 METRIC = "spmv_gflops"
 UNIT = "GFLOP/s"
 HEADLINE = "rmat24"
@@ -210,7 +233,7 @@ def run_reference(args, rank: int):
                          "convert_seconds": conv},
         "e2e": {"value": gflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_record(line)
 
 
 # ----------------------------------------------------------------------------- helpers of our arm
@@ -444,7 +467,7 @@ def run_single(args, local_rank: int):
         line["cpu_baseline"] = head["cpu_baseline"]
     if subs:
         line["workloads"] = {k: {kk: vv for kk, vv in v.items() if kk != "cpu_baseline"} for k, v in subs.items()}
-    print(json.dumps(line))
+    emit_record(line)
 
 
 # ----------------------------------------------------------------------------- our arm, N > 1
@@ -471,7 +494,7 @@ def run_multi(args, rank: int, world: int, local_rank: int):
         big_rmat = 28
     elif args.workload.startswith("rmat:") and int(args.workload.split(":")[1]) >= 26:
         big_rmat = int(args.workload.split(":")[1])
-    full = None
+    full = full_all = row_delim_all = None
     if big_rmat is not None:
         # config 5: too large to build on one GPU -- every rank generates only its own row shard
         from cvr_b200 import gen
@@ -489,6 +512,7 @@ def run_multi(args, rank: int, world: int, local_rank: int):
         n_rows_total, n_cols = full.n_rows, full.n_cols
         cuts = shard.partition_rows_by_nnz_torch(full.row_delim, world, args.row_weight)
         mine = shard.shard_device_csr(full, cuts[rank], cuts[rank + 1])
+        full_all, row_delim_all = full, full.row_delim  # every rank keeps the matrix until the shards are final
         if rank != 0:
             full = None  # rank 0 keeps the whole CSR: it is the parity reference
     torch.cuda.synchronize()
@@ -498,18 +522,69 @@ def run_multi(args, rank: int, world: int, local_rank: int):
     del mine
     torch.cuda.empty_cache()
 
-    exchange = RowShardExchange(cuts, rank, world, dev)
     stream = torch.cuda.current_stream()
     g = torch.Generator(device=dev).manual_seed(99)
     x0 = torch.rand(n_cols + 1, generator=g, device=dev, dtype=torch.float64) - 0.5
     x0[0] = 0.0
     x = x0.clone()
-    y = torch.zeros(info["n_rows"] + 1, dtype=torch.float64, device=dev)
 
     publisher = None
     if args.exchange == "peer":
         publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange)
         publisher.set_x(x)
+
+    # ---- shard balance from MEASURED sweep times (set-up, untimed): nnz (+ w per row) is a model; the parts
+    # with many short rows sweep longer than the hub-row parts of equal nnz and the slowest part sets the step.
+    # Each round times the sweep of every rank inside the real iteration (publishing included), re-cuts the rows
+    # into parts of equal measured cost (shard.rebalance_cuts) and rebuilds the shards.
+    balance_log = []
+    rounds = args.rebalance if (big_rmat is None and args.exchange == "peer") else 0
+
+    def rebuild(new_cuts):
+        nonlocal m, info, publisher, cuts
+        publisher.close()
+        m.close()
+        cuts = new_cuts
+        part = shard.shard_device_csr(full_all, cuts[rank], cuts[rank + 1])
+        m = cvr_b200.CvrMatrix(part, args.chunks, local_rank)
+        info = m.info
+        del part
+        torch.cuda.empty_cache()
+        publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange)
+        publisher.set_x(x)
+
+    best = None  # (slowest rank's sweep, cuts) of the best partition measured
+    for rnd in (range(rounds + 1) if rounds > 0 else ()):
+        for _ in range(3):
+            publisher.step(None, stream.cuda_stream)
+        m.set_kernel_timing(True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        for _ in range(6):
+            publisher.step(None, stream.cuda_stream)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ksecs, kl = m.kernel_timing()
+        m.set_kernel_timing(False)
+        times = [None] * world
+        dist.all_gather_object(times, ksecs / max(kl, 1))
+        cuts = [int(c) for c in cuts]
+        balance_log.append({"cuts": cuts, "sweep_us": [round(t * 1e6, 1) for t in times]})
+        if best is None or max(times) < best[0]:
+            best = (max(times), cuts)
+        if rnd == rounds or max(times) <= 1.03 * (sum(times) / world):
+            break
+        new_cuts = shard.rebalance_cuts(row_delim_all, cuts, times, args.row_weight, damping=args.rebalance_damping)
+        if new_cuts == cuts:
+            break
+        rebuild(new_cuts)
+    if best is not None and best[1] != cuts:
+        rebuild(best[1])  # a re-cut that measured worse than an earlier partition is not kept
+    del full_all, row_delim_all
+    torch.cuda.empty_cache()
+
+    exchange = RowShardExchange(cuts, rank, world, dev)
+    y = torch.zeros(info["n_rows"] + 1, dtype=torch.float64, device=dev)
 
     def step():
         if publisher is not None:
@@ -633,7 +708,8 @@ def run_multi(args, rank: int, world: int, local_rank: int):
             "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "n_rows": n_rows_total, "nnz": nnz_true_total,
                        "chunks_per_gpu": info["n_chunks"], "iterated_x_from_y": True,
-                       "shard_balance": "nnz" if not args.row_weight else f"nnz + {args.row_weight:g} per non-empty row",
+                       "shard_balance": ("nnz" if not args.row_weight else f"nnz + {args.row_weight:g} per non-empty row") + (
+                           f", then {len(balance_log)} round(s) of re-cutting by measured sweep time" if balance_log else ""),
                        "l2": "inputs exceed L2 (no flush)",
                        "step": "sweep kernel (programmatic dependent launch)" + (
                            " publishing y rows into every peer's x over NVLink + accumulated-rows publish + flag barrier"
@@ -650,14 +726,14 @@ def run_multi(args, rank: int, world: int, local_rank: int):
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "parity": parity,
             "clocks": clocks.summary(),
-            "extra": {"per_rank_sweep_us_rows_nnz_records": allk,
+            "extra": {"per_rank_sweep_us_rows_nnz_records": allk, "shard_balance_rounds": balance_log,
                       "peer_bytes_sent_per_step_rank0": publisher.bytes_sent_per_iteration() if publisher else None,
                       "nvlink_ingress_bytes_per_gpu": ingress,
                       "nvlink_ingress_bound_us": {"at_900_GBs_nominal": ingress / 900e9 * 1e6,
                                                   "at_770_GBs_measured": ingress / 770e9 * 1e6},
                       "convert": conversion_record(info, peak), "n_records": info["n_records"]},
         }
-        print(json.dumps(line))
+        emit_record(line)
     if publisher is not None:
         publisher.close()
     m.close()
@@ -681,11 +757,16 @@ def main():
                     help="N > 1: balance shards by nnz + W per non-empty row instead of nnz alone (0 = nnz, the spec). "
                          "Default: 0 up to 4 GPUs, 4 from 8 GPUs on -- the cost model fitted to the measured per-rank "
                          "sweep times on R-MAT-24 (profiles/r02_strong_scaling_rmat24.txt)")
+    ap.add_argument("--rebalance", type=int, default=3,
+                    help="N > 1: rounds of re-cutting the row shards by MEASURED per-rank sweep time before the timed "
+                         "region (0 = keep the nnz / row-weight partition)")
+    ap.add_argument("--rebalance-damping", type=float, default=1.0)
     ap.add_argument("--dense-exchange", action="store_true",
                     help="peer exchange: publish every row to every GPU instead of only to the GPUs that read it")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: y->x exchange fused into the SpMV kernel over peer memory, or NCCL all-gather")
     args = ap.parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -91,6 +91,47 @@ def partition_rows_by_nnz_torch(row_delim, n_parts: int, row_weight: float = 0.0
     return cuts
 
 
+def rebalance_cuts(row_delim, cuts, seconds, row_weight: float = 0.0, damping: float = 1.0):
+    """New cut points from MEASURED per-part sweep times (works on numpy arrays and torch tensors).
+
+    nnz (+ row_weight per non-empty row) is only a model of what a shard costs: on skewed matrices the parts
+    with many short rows sweep up to 1.5x longer than the hub-row parts of equal nnz, and the slowest part sets
+    the iteration time.  Given the seconds each part of `cuts` took, every row is charged its model weight
+    scaled by (seconds of its part / model weight of its part), and the rows are re-cut into parts of equal
+    CHARGED cost -- the model keeps its shape inside a part, the measurement fixes the level between parts.
+    damping < 1 moves only that fraction of the way (a re-cut changes what the parts exchange, so the times
+    it was derived from are not exactly the times it produces).  Returns a python list like
+    partition_rows_by_nnz_torch."""
+    import torch
+    rd = torch.as_tensor(row_delim).to(torch.int64)
+    n_rows = rd.shape[0] - 2
+    n_parts = len(cuts) - 1
+    if len(seconds) != n_parts:
+        raise ValueError("one time per part")
+    w = (rd[2:] - rd[1:-1]).to(torch.float64)          # model weight of rows 1..n_rows
+    if row_weight:
+        w = w + (w > 0).to(torch.float64) * float(row_weight)
+    cost = torch.empty_like(w)
+    mean = sum(float(t) for t in seconds) / n_parts
+    for g in range(n_parts):
+        a, b = int(cuts[g]) - 1, int(cuts[g + 1]) - 1  # 0-based slice of part g in w
+        if b <= a:
+            continue
+        wg = float(w[a:b].sum())
+        level = mean + damping * (float(seconds[g]) - mean)
+        cost[a:b] = w[a:b] * (level / wg if wg > 0 else 0.0)
+    cum = torch.cumsum(cost, 0)                        # cost of rows 1..r
+    total = float(cum[-1]) if n_rows > 0 else 0.0
+    out = [1]
+    for g in range(1, n_parts):
+        target = torch.tensor([total * g / n_parts], dtype=torch.float64, device=cum.device)
+        # rows 1..r cost >= target for the first time at r: part g starts at the row after
+        r = int(torch.searchsorted(cum, target, right=False)) + 2
+        out.append(min(max(r, out[-1]), n_rows + 1))
+    out.append(n_rows + 1)
+    return out
+
+
 def shard_device_csr(d, row_begin: int, row_end: int):
     """shard_csr for a DeviceCsr (torch tensors stay on their device)."""
     import torch

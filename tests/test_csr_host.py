@@ -36,3 +36,29 @@ def test_write_mtx_then_read_matrix_round_trip(native_lib, tmp_path):
     port = oracle.read_mtx(p, "port")
     np.testing.assert_array_equal(port.col, back.col)
     np.testing.assert_array_equal(port.row_delim, back.row_delim)
+
+
+def test_rebalance_cuts_from_measured_times():
+    """shard.rebalance_cuts: equal times keep the nnz partition, a slow part hands rows to its neighbours,
+    cut points stay monotone with fixed ends, and full damping to zero is the identity."""
+    from cvr_b200 import gen, shard
+    full = gen.rmat(12, 8, seed=3, row_normalise=True).to_host()
+    rd = np.asarray(full.row_delim).astype(np.int64)
+    for parts in (2, 4, 8):
+        cuts = [int(c) for c in shard.partition_rows_by_nnz(full.row_delim, parts)]
+        same = shard.rebalance_cuts(full.row_delim, cuts, [1.0] * parts)
+        assert all(abs(a - b) <= 1 for a, b in zip(same, cuts))  # (integer against floating-point targets)
+        slow_last = [1.0] * (parts - 1) + [2.0]
+        c2 = shard.rebalance_cuts(full.row_delim, cuts, slow_last)
+        assert c2[0] == 1 and c2[-1] == full.n_rows + 1 and all(a <= b for a, b in zip(c2, c2[1:]))
+        nnz_before = rd[cuts[-1]] - rd[cuts[-2]]
+        nnz_after = rd[c2[-1]] - rd[c2[-2]]
+        assert nnz_after < nnz_before  # the slow part shrinks ...
+        assert rd[c2[1]] - rd[c2[0]] > rd[cuts[1]] - rd[cuts[0]]  # ... and the others grow
+        # charged cost is equalised: (seconds per model weight of the OLD part) x weight of the new part
+        undamped = shard.rebalance_cuts(full.row_delim, cuts, slow_last, damping=0.0)
+        assert all(abs(a - b) <= 1 for a, b in zip(undamped, cuts))
+    # with a row weight the model weight of a part is nnz + w per non-empty row
+    cuts = [int(c) for c in shard.partition_rows_by_nnz(full.row_delim, 4, row_weight=3.0)]
+    same = shard.rebalance_cuts(full.row_delim, cuts, [1.0] * 4, row_weight=3.0)
+    assert all(abs(a - b) <= 1 for a, b in zip(same, cuts))
