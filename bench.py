@@ -529,8 +529,9 @@ def run_multi(args, rank: int, world: int, local_rank: int):
     x = x0.clone()
 
     publisher = None
+    mc_opt = {"auto": None, "on": True, "off": False}[args.multicast]
     if args.exchange == "peer":
-        publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange)
+        publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange, multicast=mc_opt)
         publisher.set_x(x)
 
     # ---- shard balance from MEASURED sweep times (set-up, untimed): nnz (+ w per row) is a model; the parts
@@ -550,7 +551,7 @@ def run_multi(args, rank: int, world: int, local_rank: int):
         info = m.info
         del part
         torch.cuda.empty_cache()
-        publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange)
+        publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange, multicast=mc_opt)
         publisher.set_x(x)
 
     best = None  # (slowest rank's sweep, cuts) of the best partition measured
@@ -656,6 +657,12 @@ def run_multi(args, rank: int, world: int, local_rank: int):
                 publisher.step(y, stream.cuda_stream)
                 nxt = publisher.full_x()
                 m.check_async_error()
+                if publisher.multicast:
+                    # multicast publishing is dense: EVERY rank's own buffer must hold the whole vector, bit for bit
+                    diff = (publisher.x_tensor()[1:] - nxt[1:]).abs().max().reshape(1)
+                    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+                    parity["multicast_local_copies_max_abs_diff"] = max(
+                        parity.get("multicast_local_copies_max_abs_diff", 0.0), float(diff.item()))
             else:
                 x.copy_(cur)
                 m.spmv_device(x, y, stream.cuda_stream)
@@ -683,6 +690,8 @@ def run_multi(args, rank: int, world: int, local_rank: int):
         del per_iter_x, cur
     else:
         parity["note"] = "matrix generated per shard: no whole-matrix reference on one GPU (see tests/test_gpu_multi.py)"
+    if parity.get("multicast_local_copies_max_abs_diff", 0.0) != 0.0:
+        parity["rows_failing"] += 1
     bad = torch.tensor([parity["rows_failing"]], dtype=torch.int64, device=dev)
     dist.all_reduce(bad)
 
@@ -712,8 +721,14 @@ def run_multi(args, rank: int, world: int, local_rank: int):
                            f", then {len(balance_log)} round(s) of re-cutting by measured sweep time" if balance_log else ""),
                        "l2": "inputs exceed L2 (no flush)",
                        "step": "sweep kernel (programmatic dependent launch)" + (
-                           " publishing y rows into every peer's x over NVLink + accumulated-rows publish + flag barrier"
-                           if publisher is not None else " + NCCL all-gather y->x")},
+                           (" publishing y rows with one NVSwitch multicast store per row range (multimem.st) into every GPU's x"
+                            if publisher.multicast else " publishing y rows into every peer's x over NVLink")
+                           + " + accumulated-rows publish + flag barrier"
+                           if publisher is not None else " + NCCL all-gather y->x"),
+                       "exchange": ("nccl all-gather" if publisher is None else
+                                    "multicast" if publisher.multicast else "peer stores" + (
+                                        f" (multicast unavailable: {publisher.multicast_error})"
+                                        if publisher.multicast_error else ""))},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_gflops, "unit": UNIT, "h2d_bytes_per_step": 8 * (n_cols + 1) * world,
                     "d2h_bytes_per_step": 8 * (n_rows_total + world), "steps": e2e_steps},
@@ -761,6 +776,9 @@ def main():
                     help="N > 1: rounds of re-cutting the row shards by MEASURED per-rank sweep time before the timed "
                          "region (0 = keep the nnz / row-weight partition)")
     ap.add_argument("--rebalance-damping", type=float, default=1.0)
+    ap.add_argument("--multicast", default="auto", choices=["auto", "on", "off"],
+                    help="peer exchange: publish through an NVSwitch multicast address (auto: from 3 GPUs on when "
+                         "torch symmetric memory provides one)")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="peer exchange: publish every row to every GPU instead of only to the GPUs that read it")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

@@ -39,7 +39,8 @@ class CvrInfo(C.Structure):  # cvr_info_t
 class CvrPublish(C.Structure):  # cvr_publish_t
     _fields_ = [("n_dst", C.c_int32), ("self", C.c_int32), ("mode", C.c_int32), ("row_offset", C.c_int64),
                 ("needs", C.c_void_p),
-                ("chunk_any", C.c_void_p), ("clear_next", C.c_void_p), ("dst", C.c_void_p * 8)]
+                ("chunk_any", C.c_void_p), ("clear_next", C.c_void_p), ("dst", C.c_void_p * 8),
+                ("multicast", C.c_void_p)]
 
 
 class CvrHostCsr(C.Structure):  # cvr_host_csr_t
@@ -124,7 +125,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError = ABI drift, fail loudly
             fn.restype = res
             fn.argtypes = args
-        if lib.cvr_abi_version() != 2:
+        if lib.cvr_abi_version() != 3:
             raise RuntimeError("libcvr_b200 ABI version mismatch")
         _lib = lib
     return _lib

@@ -553,6 +553,9 @@ int cvr_spmv_publish(cvr_handle_t* h, const double* x_dev, double* y_dev, const 
     p.needs = pub->needs;
     p.clear_next = pub->clear_next;
     p.chunk_any = pub->chunk_any;
+    p.mc = pub->multicast;
+    if (p.mc && ((pub->mode & 4) || pub->needs || pub->chunk_any))
+        return fail(CVR_ERR_INVALID, "multicast publishing needs mode bit 2 clear and needs = chunk_any = NULL");
     for (int k = 0; k < pub->n_dst; k++) {
         if (!pub->dst[k]) return fail(CVR_ERR_INVALID, "dst[%d] is NULL", k);
         p.dst[k] = pub->dst[k];

@@ -55,6 +55,8 @@ struct CvrPublish {
     double* clear_next;            // y of the NEXT sweep: its accumulated rows are cleared by the epilogue
                                    // (NULL: y itself).  Set when y aliases this GPU's slice of the next x.
     double* dst[CVR_MAX_PEERS];
+    double* mc;                    // multicast address of the next x (all GPUs, own included) or NULL: one
+                                   // multimem.st per published row instead of a store per destination
 };
 
 struct CvrBarrier {

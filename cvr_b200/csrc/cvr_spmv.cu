@@ -100,6 +100,13 @@ __device__ __forceinline__ uint32_t publish_mask(const CvrPublish& pub, int32_t 
     return (pub.mode & 4) ? (0xffu & ~(1u << pub.self)) : 0xffu;
 }
 
+// One store to an NVSwitch multicast address: the switch replicates it into the buffer of every GPU bound to
+// the multicast object (SASS: an ordinary STG.E.64 -- the address does the work).
+__device__ __forceinline__ void multicast_store(double* mc_addr, double value)
+{
+    asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(mc_addr), "d"(value) : "memory");
+}
+
 // A finished row that this chunk owns alone: one plain store (spmv.cpp:1204).
 template <bool kPublish>
 __device__ __forceinline__ void store_row(TileCtx& cx, int32_t row, double value)
@@ -139,6 +146,17 @@ __device__ __forceinline__ void publish_rows(const TileCtx& cx, int32_t first_ro
     __threadfence_block(); // this warp's own row stores (made by other lanes) before the re-read
     __syncwarp();
     const CvrPublish& pub = *cx.pub;
+    if (pub.mc) { // every row of the range, one coalesced multicast store per 32 rows
+        for (int32_t r0 = first_row + t; r0 <= last_row; r0 += 4 * 32) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = (r0 + 32 * u <= last_row) ? __ldcg(cx.y + r0 + 32 * u) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (r0 + 32 * u <= last_row) multicast_store(pub.mc + pub.row_offset + r0 + 32 * u, v[u]);
+        }
+        return;
+    }
     for (int32_t r0 = first_row + t; r0 <= last_row; r0 += 4 * 32) {
         double v[4];
         uint32_t nb[4];
@@ -265,7 +283,8 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
         cx.pub = &pub;
         const int32_t chunk_last_row = cp->last_row;
         const bool reads_elsewhere = kPublish && (!pub.chunk_any || pub.chunk_any[chunk]); // a peer reads some row
-        cx.scatter = reads_elsewhere && (chunk_last_row - cp->first_row + 1 > 4 * (n_rec + CVR_W));
+        // (with a multicast address a range push costs one store per 32 rows whatever the number of GPUs: always ranges)
+        cx.scatter = reads_elsewhere && !pub.mc && (chunk_last_row - cp->first_row + 1 > 4 * (n_rec + CVR_W));
         const bool publishing = reads_elsewhere && !cx.scatter; // range pushes behind the watermark
         int32_t pushed_upto = cp->first_row; // kPublish: first row of the chunk not yet sent to the peers
         cx.split1 = cp->split1;
@@ -561,6 +580,10 @@ __global__ void cvr_publish_epilogue_kernel(double* __restrict__ y, const int32_
         const int64_t g = pub.row_offset + row;
         // never-written rows: their `needs` byte is cleared (the sweep's range pushes skip them), so the
         // explicit 0.0 of the first two iterations goes to every destination but the own aliased buffer
+        if (pub.mc) {
+            multicast_store(pub.mc + g, v);
+            continue;
+        }
         const uint32_t nb = b ? publish_mask(pub, row) : ((pub.mode & 4) ? (0xffu & ~(1u << pub.self)) : 0xffu);
 #pragma unroll
         for (int p = 0; p < CVR_MAX_PEERS; p++)

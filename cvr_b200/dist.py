@@ -70,7 +70,13 @@ class PeerPublisher:
     64-byte IPC handles at set-up time.
     """
 
-    def __init__(self, matrix, cuts, rank: int, world: int, device_index: int, group=None, sparse: bool = True):
+    def __init__(self, matrix, cuts, rank: int, world: int, device_index: int, group=None, sparse: bool = True,
+                 multicast=None):
+        """multicast: True / False / None (= try it when there are more than two GPUs, fall back to peer stores).
+        With NVSwitch multicast the two x buffers are torch symmetric-memory tensors and every finished row is
+        published with ONE store to the multicast address instead of one store per reading GPU (the row-heavy
+        shards of a skewed matrix otherwise spend their load/store slots on up to 7 copies of every row); the
+        exchange is then dense and y is a buffer of its own."""
         import ctypes as C
         from . import _lib
         if world > 8:
@@ -87,6 +93,17 @@ class PeerPublisher:
             ptr, handle = C.c_void_p(), C.create_string_buffer(64)
             _lib.check(self._lib.cvr_peer_alloc(device_index, n, C.byref(ptr), handle))
             return ptr.value, handle.raw
+
+        self.multicast = False
+        self.multicast_error = None
+        if multicast is None:
+            env = os.environ.get("CVR_MULTICAST", "")
+            multicast = None if env == "" else env not in ("0", "off", "no")
+        if world > 1 and (multicast or (multicast is None and world > 2)):
+            self._setup_multicast(group, required=bool(multicast))
+        if self.multicast:
+            self._init_multicast_descriptors(alloc, group)
+            return
 
         self._own = []      # (ptr, handle) of X[0], X[1], flags
         for n in (nbytes, nbytes, 4 * 64):
@@ -150,6 +167,83 @@ class PeerPublisher:
         self._last_y = None
         dist.barrier(group=group)
 
+    # ---- NVSwitch multicast flavour -------------------------------------------------------------------
+    def _setup_multicast(self, group, required: bool) -> None:
+        """Both x buffers as symmetric-memory tensors with a multicast mapping; every rank must reach the same
+        verdict, so failures are agreed on with an all-reduce before anything depends on them."""
+        dev = torch.device("cuda", self.dev)
+        ok, err, bufs, hdls = 1, None, [], []
+        def agreed(ok_here: int) -> bool:
+            flag = torch.tensor([ok_here], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            return int(flag.item()) == 1
+
+        try:  # stage 1, local: allocate (a rank that fails here must not leave the others in the rendezvous)
+            import torch.distributed._symmetric_memory as symm
+            g = group if group is not None else dist.group.WORLD
+            bufs = [symm.empty(self.n_rows + 1, dtype=torch.float64, device=dev) for _ in range(2)]
+        except Exception as e:  # noqa: BLE001 -- any failure means "use peer stores"
+            ok, err = 0, f"{type(e).__name__}: {e}"
+        if agreed(ok):
+            try:  # stage 2, collective: exchange the handles, map the peers and the multicast object
+                for t in bufs:
+                    h = symm.rendezvous(t, g)
+                    if not int(h.multicast_ptr):
+                        raise RuntimeError("symmetric memory has no multicast mapping on this system")
+                    t.zero_()
+                    hdls.append(h)
+            except Exception as e:  # noqa: BLE001
+                ok, err = 0, f"{type(e).__name__}: {e}"
+        else:
+            ok = 0
+        if agreed(ok):
+            self.multicast, self._mc_bufs, self._mc_hdls = True, bufs, hdls
+            return
+        self.multicast_error = err or "a peer could not set up multicast"
+        del bufs, hdls
+        if required:
+            raise RuntimeError(f"NVSwitch multicast requested but unavailable: {self.multicast_error}")
+
+    def _init_multicast_descriptors(self, alloc, group) -> None:
+        C, _lib = self._C, self._libmod
+        rank, world = self.rank, self.world
+        self._own = [alloc(4 * 64)]  # the flag array still travels as a CUDA IPC handle
+        handles = [None] * world
+        dist.all_gather_object(handles, self._own[0][1], group=group)
+        self._opened, flags = [], []
+        for r in range(world):
+            if r == rank:
+                flags.append(self._own[0][0])
+                continue
+            ptr = C.c_void_p()
+            _lib.check(self._lib.cvr_peer_open(self.dev, handles[r], C.byref(ptr)))
+            flags.append(ptr.value)
+            self._opened.append(ptr.value)
+        # ptrs[r] = [X0, X1, flags] of rank r as seen from this process (peer-mapped unicast addresses)
+        self.ptrs = [[int(self._mc_hdls[0].buffer_ptrs[r]), int(self._mc_hdls[1].buffer_ptrs[r]), flags[r]]
+                     for r in range(world)]
+        self.needs = None
+        self.y_local = torch.zeros(self.n_local + 1, dtype=torch.float64, device=torch.device("cuda", self.dev))
+        self.pub = []
+        for parity in (0, 1):
+            p = _lib.CvrPublish()
+            p.n_dst = world
+            p.self = rank
+            p.mode = int(os.environ.get("CVR_PUBLISH_MODE", "0")) & ~4  # y is a buffer of its own
+            p.row_offset = self.cuts[rank] - 1
+            p.needs = None
+            p.chunk_any = None
+            p.clear_next = None
+            for r in range(world):
+                p.dst[r] = self.ptrs[r][parity]
+            p.multicast = int(self._mc_hdls[parity].multicast_ptr)
+            self.pub.append(p)
+        self._flags = (C.c_void_p * world)(*flags)
+        self.epoch = 0
+        self.k = 0
+        self._reset_k = 0
+        dist.barrier(group=group)
+
     def x_tensor(self, parity=None):
         """The local x buffer of the given parity (default: the one the next iteration reads) as a
         torch tensor view (n_rows + 1 doubles)."""
@@ -176,8 +270,11 @@ class PeerPublisher:
             for p in self.pub:
                 p.mode |= 2
         self.epoch += 1
-        y_alias = self.ptrs[self.rank][nxt] + 8 * (self.cuts[self.rank] - 1)  # y[r] == x_next[lo - 1 + r]
-        self.m.spmv_publish(self.ptrs[self.rank][cur], y_alias, pub, self._flags, self.rank, self.world,
+        if self.multicast:
+            y_ptr = self.y_local.data_ptr()
+        else:
+            y_ptr = self.ptrs[self.rank][nxt] + 8 * (self.cuts[self.rank] - 1)  # y[r] == x_next[lo - 1 + r]
+        self.m.spmv_publish(self.ptrs[self.rank][cur], y_ptr, pub, self._flags, self.rank, self.world,
                             self.epoch, self.k > self._reset_k, stream)
         self.k += 1
 
@@ -198,6 +295,8 @@ class PeerPublisher:
 
     def bytes_sent_per_iteration(self) -> int:
         """Bytes this rank stores into PEER memory per iteration."""
+        if self.multicast:
+            return 8 * self.n_local  # one copy leaves this GPU; the switch replicates it
         if self.needs is None:
             return 8 * self.n_local * (self.world - 1)
         return 8 * sum(n for q, n in enumerate(self.needed_rows) if q != self.rank)
@@ -212,6 +311,8 @@ class PeerPublisher:
         for p, _ in self._own:
             self._lib.cvr_peer_free(self.dev, p)
         self._own = []
+        if self.multicast:
+            self._mc_hdls, self._mc_bufs = [], []  # symmetric memory is released with its tensors
 
 
 class _RawCudaArray:

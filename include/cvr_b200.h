@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CVR_B200_ABI_VERSION 2
+#define CVR_B200_ABI_VERSION 3
 #define CVR_LANES 8 /* SIMD_LEN for fp64, spmv.cpp:43 -- fixed by the bit-exact contract */
 
 typedef enum cvr_status {
@@ -169,6 +169,11 @@ typedef struct cvr_publish {
                                  the push), or NULL */
     double* clear_next;  /* NULL, or the y of the NEXT iteration (see mode bit 2) */
     double* dst[CVR_MAX_PEERS];
+    double* multicast;   /* NULL, or ONE NVSwitch multicast address of the next x that maps every GPU's buffer
+                            (own included; e.g. torch symmetric memory's multicast_ptr): a finished row is then
+                            published with a single multimem.st instead of n_dst - 1 peer stores, always in
+                            contiguous ranges.  Requires mode bit 2 clear (y_dev is a buffer of its own) and
+                            needs = chunk_any = NULL.  ABI v3. */
 } cvr_publish_t;
 /* One iteration = at most three kernels on cuda_stream: [clear the accumulated rows of y, unless
  * y_is_clear] + the SpMV sweep that pushes finished rows to every dst + one epilogue kernel

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     for n in names:
         assert hasattr(native_lib, n), f"{n} declared in include/cvr_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header drifted apart"
-    assert native_lib.cvr_abi_version() == 2
+    assert native_lib.cvr_abi_version() == 3
 
 
 def test_sm100a_code_is_in_the_library(native_lib):
