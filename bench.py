@@ -498,8 +498,11 @@ def run_multi(args, rank: int, world: int, local_rank: int):
     if big_rmat is not None:
         # config 5: too large to build on one GPU -- every rank generates only its own row shard
         from cvr_b200 import gen
-        mine, cuts, nt = gen.rmat_shard(big_rmat, 16, rank, world, dev, row_normalise=True,
-                                        row_weight=args.row_weight)
+        mine, cuts, nt, row_delim_all = gen.rmat_shard(big_rmat, 16, rank, world, dev, row_normalise=True,
+                                                       row_weight=args.row_weight, return_counts=True)
+
+        def make_shard(new_cuts):
+            return gen.rmat_shard(big_rmat, 16, rank, world, dev, row_normalise=True, cuts=new_cuts)[0]
         tot = torch.tensor([nt], dtype=torch.int64, device=dev)
         dist.all_reduce(tot)
         nnz_true_total = int(tot.item())
@@ -513,12 +516,16 @@ def run_multi(args, rank: int, world: int, local_rank: int):
         cuts = shard.partition_rows_by_nnz_torch(full.row_delim, world, args.row_weight)
         mine = shard.shard_device_csr(full, cuts[rank], cuts[rank + 1])
         full_all, row_delim_all = full, full.row_delim  # every rank keeps the matrix until the shards are final
+
+        def make_shard(new_cuts):
+            return shard.shard_device_csr(full_all, new_cuts[rank], new_cuts[rank + 1])
         if rank != 0:
             full = None  # rank 0 keeps the whole CSR: it is the parity reference
     torch.cuda.synchronize()
 
     m = cvr_b200.CvrMatrix(mine, args.chunks, local_rank)
     info = m.info
+    shard_csr_kept = [mine if big_rmat is not None else None]
     del mine
     torch.cuda.empty_cache()
 
@@ -539,16 +546,20 @@ def run_multi(args, rank: int, world: int, local_rank: int):
     # Each round times the sweep of every rank inside the real iteration (publishing included), re-cuts the rows
     # into parts of equal measured cost (shard.rebalance_cuts) and rebuilds the shards.
     balance_log = []
-    rounds = args.rebalance if (big_rmat is None and args.exchange == "peer") else 0
+    rounds = args.rebalance if args.exchange == "peer" else 0
 
     def rebuild(new_cuts):
         nonlocal m, info, publisher, cuts
         publisher.close()
         m.close()
         cuts = new_cuts
-        part = shard.shard_device_csr(full_all, cuts[rank], cuts[rank + 1])
+        shard_csr_kept[0] = None
+        torch.cuda.empty_cache()
+        part = make_shard(cuts)
         m = cvr_b200.CvrMatrix(part, args.chunks, local_rank)
         info = m.info
+        if big_rmat is not None:
+            shard_csr_kept[0] = part  # the parity check of a per-shard matrix verifies every rank's own rows
         del part
         torch.cuda.empty_cache()
         publisher = PeerPublisher(m, cuts, rank, world, local_rank, sparse=not args.dense_exchange, multicast=mc_opt)
@@ -688,8 +699,35 @@ def run_multi(args, rank: int, world: int, local_rank: int):
                 worst = max(worst, float((xa[1:] - per_iter_x[it][1:]).abs().max().item()) / scale)
             parity["peer_vs_nccl_max_abs_over_max"] = worst
         del per_iter_x, cur
+    elif publisher is not None:
+        # the matrix only exists as row shards: EVERY rank checks its own rows against the CSR product of its
+        # shard with the assembled x of the previous iteration (three iterations: a row a peer failed to deliver
+        # shows up as a wrong product in the next one)
+        parity["tolerance"] = ("per row |dy| <= 1e-12 * sum|a x|, every rank verifies its own shard's rows against the "
+                               "device CSR product, one iteration at a time")
+        mine_csr = shard_csr_kept[0]
+        cur = x0.clone()
+        lo = cuts[rank]
+        for it in range(3):
+            if it == 0:
+                publisher.set_x(cur)
+            publisher.step(y, stream.cuda_stream)
+            nxt = publisher.full_x()
+            m.check_async_error()
+            y_mine = nxt[lo - 1:lo + info["n_rows"]].clone()  # y_mine[r] = x_next[lo - 1 + r], local rows 1..n
+            r = cvr_b200.verify_csr(mine_csr, cur, y_mine, REL_TOL, check_row0=False)
+            parity["rows_failing"] += r["rows_failing"]
+            parity["max_rel"] = max(parity["max_rel"], r["max_rel"])
+            parity["iterations_checked"] += 1
+            cur = nxt
+            del y_mine
+        del cur, nxt
+        mx = torch.tensor([parity["max_rel"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        parity["max_rel"] = float(mx.item())
     else:
-        parity["note"] = "matrix generated per shard: no whole-matrix reference on one GPU (see tests/test_gpu_multi.py)"
+        parity["note"] = "matrix generated per shard, NCCL exchange: not verified here (see tests/test_gpu_multi.py)"
+    shard_csr_kept[0] = None
     if parity.get("multicast_local_copies_max_abs_diff", 0.0) != 0.0:
         parity["rows_failing"] += 1
     bad = torch.tensor([parity["rows_failing"]], dtype=torch.int64, device=dev)
@@ -777,8 +815,8 @@ def main():
                          "region (0 = keep the nnz / row-weight partition)")
     ap.add_argument("--rebalance-damping", type=float, default=1.0)
     ap.add_argument("--multicast", default="auto", choices=["auto", "on", "off"],
-                    help="peer exchange: publish through an NVSwitch multicast address (auto: from 3 GPUs on when "
-                         "torch symmetric memory provides one)")
+                    help="peer exchange: publish through an NVSwitch multicast address (torch symmetric memory); "
+                         "auto = CVR_MULTICAST, default off")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="peer exchange: publish every row to every GPU instead of only to the GPUs that read it")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

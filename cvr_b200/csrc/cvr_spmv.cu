@@ -440,8 +440,9 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
             lane_carry = __shfl_sync(FULL, out, 24 + l);
             if (has) emit<kPublish>(cx, head + cin, p0 + b_first * CVR_W, s_wb[w][b_first][t], carry_slot);
             __syncwarp(); // slots are reused by the next tile's delivery
-            if (kPublish && publishing) {
+            if (kPublish && publishing && ((tile & 3) == 3 || tile + 1 == n_tiles)) {
                 // watermark: every row up to min over the SIMD lanes of the lane's latest stored row is final
+                // (taken every fourth tile: five shuffles through the unit the sweep is bound by)
                 int32_t f = cx.last_done;
                 f = max(f, __shfl_xor_sync(FULL, f, 8));
                 f = max(f, __shfl_xor_sync(FULL, f, 16)); // latest row of SIMD lane l (any of its four walkers)

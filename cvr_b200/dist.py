@@ -72,7 +72,8 @@ class PeerPublisher:
 
     def __init__(self, matrix, cuts, rank: int, world: int, device_index: int, group=None, sparse: bool = True,
                  multicast=None):
-        """multicast: True / False / None (= try it when there are more than two GPUs, fall back to peer stores).
+        """multicast: True / False / None (= CVR_MULTICAST, default off: measured slower than the footprint-sparse
+        peer stores on R-MAT-24).
         With NVSwitch multicast the two x buffers are torch symmetric-memory tensors and every finished row is
         published with ONE store to the multicast address instead of one store per reading GPU (the row-heavy
         shards of a skewed matrix otherwise spend their load/store slots on up to 7 copies of every row); the
@@ -97,10 +98,9 @@ class PeerPublisher:
         self.multicast = False
         self.multicast_error = None
         if multicast is None:
-            env = os.environ.get("CVR_MULTICAST", "")
-            multicast = None if env == "" else env not in ("0", "off", "no")
-        if world > 1 and (multicast or (multicast is None and world > 2)):
-            self._setup_multicast(group, required=bool(multicast))
+            multicast = os.environ.get("CVR_MULTICAST", "0") not in ("", "0", "off", "no")
+        if world > 1 and multicast:
+            self._setup_multicast(group, required=True)
         if self.multicast:
             self._init_multicast_descriptors(alloc, group)
             return

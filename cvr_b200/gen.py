@@ -158,13 +158,16 @@ def random_sparse(n_rows: int, n_cols: int, nnz: int, device="cpu", seed: int = 
 
 def rmat_shard(scale: int, edge_factor: int, rank: int, world: int, device="cpu", seed: int = 3,
                abcd=(0.57, 0.19, 0.19, 0.05), row_normalise: bool = True, batch: int = 1 << 26,
-               row_weight: float = 0.0):
+               row_weight: float = 0.0, cuts=None, return_counts: bool = False):
     """Row shard `rank` of `world` of an R-MAT matrix too large to build on one GPU (config 5:
     scale 28, 4.3e9 edges).  Every rank draws the same edge stream twice from per-batch seeds
     (pass 1: row histogram -> nnz-balanced cuts, the rule of cvr_b200.shard; pass 2: keep only the
     rows it owns), so no edge ever leaves the GPU that generated it and no rank holds more than its
     own shard.  Returns (DeviceCsr with LOCAL rows 1..n_local and GLOBAL columns, cuts list,
-    entries in this shard before padding)."""
+    entries in this shard before padding).  With `cuts` given (e.g. from shard.rebalance_cuts) pass 1 is
+    skipped and exactly those row ranges are built; return_counts appends the row histogram of pass 1 as a
+    delimiter-like int64 array of n + 2 entries (rd[r + 1] - rd[r] = edges drawn for row r, duplicates
+    included), the row weights shard.rebalance_cuts works from."""
     dev = torch.device(device)
     n = 1 << scale
     total = edge_factor << scale
@@ -183,24 +186,33 @@ def rmat_shard(scale: int, edge_factor: int, rank: int, world: int, device="cpu"
             col = (col << 1) | (((u >= a) & (u < a + b)) | (u >= a + b + c)).to(torch.int64)
         return r + 1, col + 1
 
-    counts = torch.zeros(n + 2, dtype=torch.int64, device=dev)
-    for i in range(n_batches):
-        r, _ = draw(i)
-        counts += torch.bincount(r, minlength=n + 2)
-        del r
-    if row_weight:  # balance nnz + row_weight per non-empty row (shard.partition_rows_by_nnz)
-        counts = counts + ((counts > 0).to(torch.float64) * float(row_weight)).to(torch.int64)
-    ends = torch.cumsum(counts, 0)  # ends[r] = (weighted) edges in rows <= r
-    del counts
-    weighted_total = int(ends[-1])
-    cuts = [1]
-    for gidx in range(1, world):
-        target = torch.tensor([(weighted_total * gidx) // world], dtype=torch.int64, device=dev)
-        # first row whose start (= ends[row-1]) is >= target
-        row = int(torch.searchsorted(ends, target, right=False)) + 1
-        cuts.append(min(max(row, cuts[-1]), n + 1))
-    cuts.append(n + 1)
-    del ends
+    row_delim_like = None
+    if cuts is None:
+        counts = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+        for i in range(n_batches):
+            r, _ = draw(i)
+            counts += torch.bincount(r, minlength=n + 2)
+            del r
+        if return_counts:
+            row_delim_like = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+            row_delim_like[2:] = torch.cumsum(counts[1:n + 1], 0)
+        if row_weight:  # balance nnz + row_weight per non-empty row (shard.partition_rows_by_nnz)
+            counts = counts + ((counts > 0).to(torch.float64) * float(row_weight)).to(torch.int64)
+        ends = torch.cumsum(counts, 0)  # ends[r] = (weighted) edges in rows <= r
+        del counts
+        weighted_total = int(ends[-1])
+        cuts = [1]
+        for gidx in range(1, world):
+            target = torch.tensor([(weighted_total * gidx) // world], dtype=torch.int64, device=dev)
+            # first row whose start (= ends[row-1]) is >= target
+            row = int(torch.searchsorted(ends, target, right=False)) + 1
+            cuts.append(min(max(row, cuts[-1]), n + 1))
+        cuts.append(n + 1)
+        del ends
+    else:
+        cuts = [int(c) for c in cuts]
+        if len(cuts) != world + 1 or cuts[0] != 1 or cuts[-1] != n + 1:
+            raise ValueError("cuts must run from 1 to n_rows + 1 with one part per rank")
     lo, hi = cuts[rank], cuts[rank + 1]
     kept = []
     for i in range(n_batches):
@@ -213,4 +225,6 @@ def rmat_shard(scale: int, edge_factor: int, rank: int, world: int, device="cpu"
     keys = torch.cat(kept) if kept else torch.zeros(0, dtype=torch.int64, device=dev)
     del kept
     d = _finish(keys, n_local, n, g, row_normalise)
+    if return_counts:
+        return d, cuts, d.nnz_true, row_delim_like
     return d, cuts, d.nnz_true

@@ -62,3 +62,28 @@ def test_rebalance_cuts_from_measured_times():
     cuts = [int(c) for c in shard.partition_rows_by_nnz(full.row_delim, 4, row_weight=3.0)]
     same = shard.rebalance_cuts(full.row_delim, cuts, [1.0] * 4, row_weight=3.0)
     assert all(abs(a - b) <= 1 for a, b in zip(same, cuts))
+
+
+def test_rmat_shard_with_given_cuts_and_row_histogram():
+    """gen.rmat_shard (config 5's per-shard generator): the shards of its own nnz-balanced cuts tile the matrix,
+    passing those cuts back reproduces them exactly, other cuts (e.g. from shard.rebalance_cuts) give shards of
+    exactly those row ranges with the same total, and the row histogram has the delimiter shape."""
+    import torch
+    from cvr_b200 import gen, shard
+    scale, world = 10, 3
+    first = [gen.rmat_shard(scale, 8, r, world, "cpu", seed=5, return_counts=True) for r in range(world)]
+    cuts = first[0][1]
+    assert all(f[1] == cuts for f in first) and cuts[0] == 1 and cuts[-1] == (1 << scale) + 1
+    rd = first[0][3]
+    assert rd.shape[0] == (1 << scale) + 2 and int(rd[0]) == 0 and int(rd[1]) == 0 and int(rd[-1]) == 8 << scale
+    total = sum(f[2] for f in first)
+    again = [gen.rmat_shard(scale, 8, r, world, "cpu", seed=5, cuts=cuts) for r in range(world)]
+    for a, b in zip(first, again):
+        assert torch.equal(a[0].col, b[0].col) and torch.equal(a[0].val, b[0].val) and torch.equal(a[0].row_delim, b[0].row_delim)
+    moved = shard.rebalance_cuts(rd, cuts, [1.0, 1.0, 2.0])
+    assert moved != cuts
+    other = [gen.rmat_shard(scale, 8, r, world, "cpu", seed=5, cuts=moved) for r in range(world)]
+    assert sum(o[2] for o in other) == total
+    assert [o[0].n_rows for o in other] == [max(moved[r + 1] - moved[r], 1) for r in range(world)]
+    with pytest.raises(ValueError):
+        gen.rmat_shard(scale, 8, 0, world, "cpu", seed=5, cuts=[1, 5, 9])
