@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -61,6 +62,104 @@ double wall_seconds()
     return duration<double>(steady_clock::now().time_since_epoch()).count();
 }
 
+// CVR_CREATE_TRACE=1: wall time of every phase of cvr_create* on stderr (where does "Pre-processing time" go?)
+struct PhaseTrace {
+    bool on;
+    double t;
+    PhaseTrace() : on(false), t(0.0)
+    {
+        const char* e = getenv("CVR_CREATE_TRACE");
+        on = e && *e == '1';
+        if (on) t = wall_seconds();
+    }
+    void mark(const char* what)
+    {
+        if (!on) return;
+        const double now = wall_seconds();
+        fprintf(stderr, "[cvr create] %-34s %9.3f ms\n", what, (now - t) * 1e3);
+        t = now;
+    }
+};
+
+bool pool_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("CVR_NO_POOL");
+        return !(e && *e == '1');
+    }();
+    return on;
+}
+
+// ---- pinned staging ring for the upload of a HOST CSR: pageable cudaMemcpy runs at 3-10 GB/s on the test boxes
+// (one driver thread copies into its own staging buffer); here OpenMP threads fill pinned slots while the DMA of
+// the previous slots is in flight.
+struct StagingRing {
+    static constexpr int SLOTS = 4;
+    static constexpr size_t SLOT_BYTES = (size_t)8 << 20;
+    char* buf[SLOTS] = {};
+    cudaEvent_t ev[SLOTS] = {};
+    bool used[SLOTS] = {};
+    int next = 0;
+    bool ok = false;
+    std::mutex busy;
+};
+
+StagingRing* staging_ring()
+{
+    static StagingRing ring;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* e = getenv("CVR_NO_STAGING");
+        if (e && *e == '1') return;
+        for (int k = 0; k < StagingRing::SLOTS; k++) {
+            if (cudaHostAlloc(reinterpret_cast<void**>(&ring.buf[k]), StagingRing::SLOT_BYTES, cudaHostAllocPortable) !=
+                    cudaSuccess ||
+                cudaEventCreateWithFlags(&ring.ev[k], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                return; // no ring: plain cudaMemcpy
+            }
+        }
+        ring.ok = true;
+    });
+    return ring.ok ? &ring : nullptr;
+}
+
+// host (pageable or pinned) -> device on `stream`; returns after the last piece has been QUEUED, the caller
+// synchronises the stream before it lets go of `src`
+cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t stream)
+{
+    StagingRing* ring = bytes >= ((size_t)1 << 20) ? staging_ring() : nullptr;
+    std::unique_lock<std::mutex> lock;
+    if (ring) {
+        lock = std::unique_lock<std::mutex>(ring->busy, std::try_to_lock);
+        if (!lock.owns_lock()) ring = nullptr; // another thread (sharded host) is uploading: do not queue behind it
+    }
+    if (!ring) {
+        const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+        return e;
+    }
+    const char* s8 = static_cast<const char*>(src);
+    char* d8 = static_cast<char*>(dst);
+    for (size_t off = 0; off < bytes; off += StagingRing::SLOT_BYTES) {
+        const size_t n = bytes - off < StagingRing::SLOT_BYTES ? bytes - off : StagingRing::SLOT_BYTES;
+        const int k = ring->next;
+        ring->next = (k + 1) % StagingRing::SLOTS;
+        cudaError_t e = cudaSuccess;
+        if (ring->used[k] && (e = cudaEventSynchronize(ring->ev[k])) != cudaSuccess) return e;
+        const long pieces = (long)((n + ((size_t)1 << 20) - 1) >> 20);
+#pragma omp parallel for schedule(static) num_threads(8)
+        for (long q = 0; q < pieces; q++) {
+            const size_t a = (size_t)q << 20, len = n - a < ((size_t)1 << 20) ? n - a : ((size_t)1 << 20);
+            memcpy(ring->buf[k] + a, s8 + off + a, len);
+        }
+        if ((e = cudaMemcpyAsync(d8 + off, ring->buf[k], n, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(ring->ev[k], stream)) != cudaSuccess) return e;
+        ring->used[k] = true;
+    }
+    return cudaSuccess;
+}
+
+
 } // namespace
 
 struct cvr_handle {
@@ -107,15 +206,18 @@ struct cvr_handle {
         if (loop_graph) cudaGraphExecDestroy(loop_graph);
         for (cudaEvent_t e : slab_events) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
-        cudaFree(vals);
-        cudaFree(cols);
-        cudaFree(record);
-        cudaFree(chunks);
-        cudaFree(rows.boundary);
-        cudaFree(rows.empty);
-        cudaFree(done_counter);
-        cudaFree(x);
-        cudaFree(y);
+        // the arrays may still be in use by sweeps the caller queued on its own streams: one device-wide
+        // synchronisation, then stream-ordered frees back into the pool (no further blocking)
+        cudaDeviceSynchronize();
+        cvr_dev_free(vals, stream);
+        cvr_dev_free(cols, stream);
+        cvr_dev_free(record, stream);
+        cvr_dev_free(chunks, stream);
+        cvr_dev_free(rows.boundary, stream);
+        cvr_dev_free(rows.empty, stream);
+        cvr_dev_free(done_counter, stream);
+        cvr_dev_free(x, stream);
+        cvr_dev_free(y, stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
@@ -130,7 +232,7 @@ template <typename T>
 cudaError_t dev_alloc(cvr_handle* h, T** p, size_t count)
 {
     const size_t bytes = sizeof(T) * (count ? count : 1);
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+    cudaError_t e = cvr_dev_malloc(reinterpret_cast<void**>(p), bytes, h->stream);
     if (e == cudaSuccess) h->device_bytes += (int64_t)bytes;
     return e;
 }
@@ -188,6 +290,7 @@ int check_csr(const cvr_csr_t* csr, int32_t n_chunks)
 int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
 {
     const int32_t T = h->n_chunks;
+    PhaseTrace trace;
     CUDA_TRY(dev_alloc(h, &h->vals, (size_t)h->nnz));
     CUDA_TRY(dev_alloc(h, &h->cols, (size_t)h->nnz));
     CUDA_TRY(dev_alloc(h, &h->record, (size_t)h->record_ints));
@@ -202,24 +305,25 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
     int2* segments = nullptr;
     int32_t* seg_count = nullptr;
     const size_t seg_entries = (size_t)CVR_SEG_STRIDE * T + (size_t)h->n_rows + 64;
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&segments), sizeof(int2) * seg_entries));
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&seg_count), sizeof(int32_t) * ((size_t)T + 2));
+    CUDA_TRY(cvr_dev_malloc(reinterpret_cast<void**>(&segments), sizeof(int2) * seg_entries, h->stream));
+    cudaError_t e = cvr_dev_malloc(reinterpret_cast<void**>(&seg_count), sizeof(int32_t) * ((size_t)T + 2), h->stream);
     if (e != cudaSuccess) {
-        cudaFree(segments);
+        cvr_dev_free(segments, h->stream);
         return fail(CVR_ERR_CUDA, "cudaMalloc(seg_count): %s", cudaGetErrorString(e));
     }
 
     uint32_t* row_bitmap = nullptr;
     const size_t bitmap_words = (size_t)(h->n_rows + 2) / 32 + 2;
-    e = cudaMalloc(reinterpret_cast<void**>(&row_bitmap), sizeof(uint32_t) * bitmap_words);
+    e = cvr_dev_malloc(reinterpret_cast<void**>(&row_bitmap), sizeof(uint32_t) * bitmap_words, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(row_bitmap, 0, sizeof(uint32_t) * bitmap_words, h->stream);
     if (e != cudaSuccess) {
-        cudaFree(segments);
-        cudaFree(seg_count);
-        cudaFree(row_bitmap);
+        cvr_dev_free(segments, h->stream);
+        cvr_dev_free(seg_count, h->stream);
+        cvr_dev_free(row_bitmap, h->stream);
         return fail(CVR_ERR_CUDA, "cudaMalloc(row_bitmap): %s", cudaGetErrorString(e));
     }
 
+    trace.mark("device allocations (12)");
     CvrConvertArgs a{};
     a.row_bitmap = row_bitmap;
     a.csr_val = csr->val;
@@ -255,6 +359,7 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
         // allocate, synchronise and free around their three small kernels, so they are timed by the host clock
         if ((e = cudaEventRecord(h->ev2, h->stream)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
+        trace.mark("record fill + conversion kernels");
         const double tl0 = wall_seconds();
         const int listed = cvr_build_row_lists(h->chunks, T, csr->row_delim32, csr->row_delim64, h->n_rows,
                                                &h->rows, h->stream);
@@ -267,12 +372,14 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
         if ((e = cudaEventRecord(h->ev1, h->stream)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
         t_lists = wall_seconds() - tl0;
+        trace.mark("row lists");
         if ((e = cudaEventElapsedTime(&ms, h->ev0, h->ev1)) != cudaSuccess) break;
         if ((e = cudaEventElapsedTime(&ms_kernels, h->ev0, h->ev2)) != cudaSuccess) break;
     } while (0);
-    cudaFree(segments);
-    cudaFree(seg_count);
-    cudaFree(row_bitmap);
+    cvr_dev_free(segments, h->stream);
+    cvr_dev_free(seg_count, h->stream);
+    cvr_dev_free(row_bitmap, h->stream);
+    trace.mark("free scratch");
     if (rc != CVR_OK) return rc;
     if (e != cudaSuccess) return fail(CVR_ERR_CUDA, "conversion failed: %s", cudaGetErrorString(e));
     h->convert_kernel_seconds = ms_kernels * 1e-3;
@@ -284,6 +391,7 @@ int convert_on_device(cvr_handle* h, const cvr_csr_t* csr)
                         cudaMemcpyDeviceToHost));
     h->n_records = 0;
     for (const CvrChunk& c : h->host_chunks) h->n_records += c.n_rec + CVR_W;
+    trace.mark("chunk descriptors to host");
     return CVR_OK;
 }
 
@@ -340,11 +448,14 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
         if (preloaded_device != device) {
             cvr_preload_convert_kernels();
             cvr_preload_spmv_kernels();
+            cvr_pool_setup(device);
             cudaGetLastError();
             preloaded_device = device;
         }
+        if (!csr_on_device) staging_ring(); // pinned once per process, outside the timed creation
     }
     const double t0 = wall_seconds();
+    PhaseTrace trace;
     cvr_handle* h = new (std::nothrow) cvr_handle();
     if (!h) return fail(CVR_ERR_INVALID, "out of host memory");
     h->device = device;
@@ -363,6 +474,7 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
         return fail(CVR_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
     }
 
+    trace.mark("handle, stream, events");
     cvr_csr_t dev = *csr;
     double* d_val = nullptr;
     int32_t* d_col = nullptr;
@@ -397,17 +509,18 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
     }
     if (!csr_on_device) {
         const size_t rd_bytes = (size_t)(csr->n_rows + 2) * (csr->row_delim64 ? 8 : 4);
-        if ((e = cudaMalloc(reinterpret_cast<void**>(&d_val), sizeof(double) * (size_t)csr->nnz)) == cudaSuccess &&
-            (e = cudaMalloc(reinterpret_cast<void**>(&d_col), sizeof(int32_t) * (size_t)csr->nnz)) == cudaSuccess &&
-            (e = cudaMalloc(&d_rd, rd_bytes)) == cudaSuccess &&
-            (e = cudaMemcpy(d_val, csr->val, sizeof(double) * (size_t)csr->nnz, cudaMemcpyHostToDevice)) == cudaSuccess &&
-            (e = cudaMemcpy(d_col, csr->col, sizeof(int32_t) * (size_t)csr->nnz, cudaMemcpyHostToDevice)) == cudaSuccess)
-            e = cudaMemcpy(d_rd, csr->row_delim64 ? (const void*)csr->row_delim64 : (const void*)csr->row_delim32,
-                           rd_bytes, cudaMemcpyHostToDevice);
+        if ((e = cvr_dev_malloc(reinterpret_cast<void**>(&d_val), sizeof(double) * (size_t)csr->nnz, h->stream)) == cudaSuccess &&
+            (e = cvr_dev_malloc(reinterpret_cast<void**>(&d_col), sizeof(int32_t) * (size_t)csr->nnz, h->stream)) == cudaSuccess &&
+            (e = cvr_dev_malloc(&d_rd, rd_bytes, h->stream)) == cudaSuccess &&
+            (e = upload_async(d_val, csr->val, sizeof(double) * (size_t)csr->nnz, h->stream)) == cudaSuccess &&
+            (e = upload_async(d_col, csr->col, sizeof(int32_t) * (size_t)csr->nnz, h->stream)) == cudaSuccess &&
+            (e = upload_async(d_rd, csr->row_delim64 ? (const void*)csr->row_delim64 : (const void*)csr->row_delim32,
+                              rd_bytes, h->stream)) == cudaSuccess)
+            e = cudaStreamSynchronize(h->stream); // the caller's arrays are free again when cvr_create returns
         if (e != cudaSuccess) {
-            cudaFree(d_val);
-            cudaFree(d_col);
-            cudaFree(d_rd);
+            cvr_dev_free(d_val, h->stream);
+            cvr_dev_free(d_col, h->stream);
+            cvr_dev_free(d_rd, h->stream);
             delete h;
             return fail(CVR_ERR_CUDA, "CSR upload failed: %s", cudaGetErrorString(e));
         }
@@ -418,11 +531,11 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
     } else if (ref_last_delim) {
         // the caller's device CSR is read-only: repair a private copy of the delimiters
         const size_t rd_bytes = (size_t)(csr->n_rows + 2) * (csr->row_delim64 ? 8 : 4);
-        if ((e = cudaMalloc(&d_rd, rd_bytes)) == cudaSuccess)
-            e = cudaMemcpy(d_rd, csr->row_delim64 ? (const void*)csr->row_delim64 : (const void*)csr->row_delim32,
-                           rd_bytes, cudaMemcpyDeviceToDevice);
+        if ((e = cvr_dev_malloc(&d_rd, rd_bytes, h->stream)) == cudaSuccess)
+            e = cudaMemcpyAsync(d_rd, csr->row_delim64 ? (const void*)csr->row_delim64 : (const void*)csr->row_delim32,
+                                rd_bytes, cudaMemcpyDeviceToDevice, h->stream);
         if (e != cudaSuccess) {
-            cudaFree(d_rd);
+            cvr_dev_free(d_rd, h->stream);
             delete h;
             return fail(CVR_ERR_CUDA, "delimiter copy failed: %s", cudaGetErrorString(e));
         }
@@ -436,18 +549,21 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
                                       csr->row_delim64 ? static_cast<int64_t*>(d_rd) : nullptr, csr->n_rows, csr->nnz,
                                       h->stream) < 0 ||
             cudaStreamSynchronize(h->stream) != cudaSuccess) {
-            cudaFree(d_val);
-            cudaFree(d_col);
-            cudaFree(d_rd);
+            cvr_dev_free(d_val, h->stream);
+            cvr_dev_free(d_col, h->stream);
+            cvr_dev_free(d_rd, h->stream);
             delete h;
             return fail(CVR_ERR_CUDA, "delimiter repair failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
     }
 
+    trace.mark("delimiter check + CSR upload");
     rc = convert_on_device(h, &dev);
-    cudaFree(d_val);
-    cudaFree(d_col);
-    cudaFree(d_rd);
+    trace.mark("convert_on_device (total)");
+    cvr_dev_free(d_val, h->stream);
+    cvr_dev_free(d_col, h->stream);
+    cvr_dev_free(d_rd, h->stream);
+    trace.mark("free device CSR copy");
     if (rc != CVR_OK) {
         delete h;
         return rc;
@@ -458,6 +574,41 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
 }
 
 } // namespace
+
+cudaError_t cvr_dev_malloc(void** p, size_t bytes, cudaStream_t stream)
+{
+    if (bytes == 0) bytes = 1;
+    if (pool_enabled()) {
+        const cudaError_t e = cudaMallocAsync(p, bytes, stream);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError(); // pools unsupported or exhausted: fall through to cudaMalloc
+    }
+    return cudaMalloc(p, bytes);
+}
+
+void cvr_dev_free(void* p, cudaStream_t stream)
+{
+    if (!p) return;
+    if (pool_enabled() && cudaFreeAsync(p, stream) == cudaSuccess) return;
+    cudaGetLastError();
+    cudaFree(p); // also correct for memory that came from cudaMallocAsync
+}
+
+void cvr_pool_setup(int device)
+{
+    if (!pool_enabled()) return;
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    // freed blocks stay in the pool up to this many bytes (default 0 = everything goes back to the driver at the
+    // next synchronisation, which makes every allocation a fresh mapping again); CVR_POOL_KEEP_MB overrides
+    uint64_t keep = (uint64_t)2 << 30;
+    if (const char* e = getenv("CVR_POOL_KEEP_MB")) keep = (uint64_t)atoll(e) << 20;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaGetLastError();
+}
 
 extern "C" {
 
@@ -476,6 +627,8 @@ int cvr_device_init(int device)
     CUDA_TRY(cudaFree(nullptr));
     cvr_preload_convert_kernels();
     cvr_preload_spmv_kernels();
+    cvr_pool_setup(device);
+    staging_ring();
     cudaGetLastError();
     return CVR_OK;
 }
@@ -537,7 +690,7 @@ int cvr_spmv_publish(cvr_handle_t* h, const double* x_dev, double* y_dev, const 
     b.timeout_cycles = barrier_timeout_cycles(h->device);
     if (!h->done_counter) {
         CUDA_TRY(cudaSetDevice(h->device));
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->done_counter), 4 * sizeof(unsigned int)));
+        CUDA_TRY(cvr_dev_malloc(reinterpret_cast<void**>(&h->done_counter), 4 * sizeof(unsigned int), nullptr));
         CUDA_TRY(cudaMemset(h->done_counter, 0, 4 * sizeof(unsigned int)));
     }
     b.error = h->done_counter + 1;
@@ -1028,6 +1181,8 @@ int cvr_load(const char* path, int device, cvr_handle_t** out)
         if ((e = dev_alloc(h, &h->x, (size_t)h->n_cols + 1)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->y, (size_t)h->n_rows + 1)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->done_counter, 4)) != cudaSuccess) break;
+        // stream-ordered allocations: the copies below run on the default stream
+        if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) break;
         if ((e = cudaMemset(h->done_counter, 0, 4 * sizeof(unsigned int))) != cudaSuccess) break;
     } while (0);
     if (e != cudaSuccess) {

@@ -714,9 +714,9 @@ int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t*
 {
     unsigned char* flags = nullptr;
     int32_t* counters = nullptr;
-    if (cudaMalloc(reinterpret_cast<void**>(&flags), (size_t)n_rows + 2) != cudaSuccess) return -1;
-    if (cudaMalloc(reinterpret_cast<void**>(&counters), 2 * sizeof(int32_t)) != cudaSuccess) {
-        cudaFree(flags);
+    if (cvr_dev_malloc(reinterpret_cast<void**>(&flags), (size_t)n_rows + 2, stream) != cudaSuccess) return -1;
+    if (cvr_dev_malloc(reinterpret_cast<void**>(&counters), 2 * sizeof(int32_t), stream) != cudaSuccess) {
+        cvr_dev_free(flags, stream);
         return -1;
     }
     int launched = 0, rc = 0;
@@ -738,8 +738,8 @@ int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t*
             cudaStreamSynchronize(stream) != cudaSuccess) { rc = -1; break; }
         out->n_boundary = h[0];
         out->n_empty = h[1];
-        if (cudaMalloc(reinterpret_cast<void**>(&out->boundary), sizeof(int32_t) * (size_t)(h[0] + 1)) != cudaSuccess ||
-            cudaMalloc(reinterpret_cast<void**>(&out->empty), sizeof(int32_t) * (size_t)(h[1] + 1)) != cudaSuccess) {
+        if (cvr_dev_malloc(reinterpret_cast<void**>(&out->boundary), sizeof(int32_t) * (size_t)(h[0] + 1), stream) != cudaSuccess ||
+            cvr_dev_malloc(reinterpret_cast<void**>(&out->empty), sizeof(int32_t) * (size_t)(h[1] + 1), stream) != cudaSuccess) {
             rc = -1;
             break;
         }
@@ -753,8 +753,8 @@ int cvr_build_row_lists(const CvrChunk* chunks, int32_t n_chunks, const int32_t*
         launched += 1;
         if (cudaStreamSynchronize(stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = -1;
     } while (0);
-    cudaFree(flags);
-    cudaFree(counters);
+    cvr_dev_free(flags, stream);
+    cvr_dev_free(counters, stream);
     return rc < 0 ? rc : launched;
 }
 
