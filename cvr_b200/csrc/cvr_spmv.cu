@@ -284,7 +284,10 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
         const int32_t chunk_last_row = cp->last_row;
         const bool reads_elsewhere = kPublish && (!pub.chunk_any || pub.chunk_any[chunk]); // a peer reads some row
         // (with a multicast address a range push costs one store per 32 rows whatever the number of GPUs: always ranges)
-        cx.scatter = reads_elsewhere && !pub.mc && (chunk_last_row - cp->first_row + 1 > 4 * (n_rec + CVR_W));
+        // experiment knobs in the upper mode bits (0 = default): bits 8-15 push_min_rows / 16, bits 16-23 scatter factor
+        const int32_t scatter_factor = ((pub.mode >> 16) & 0xff) ? ((pub.mode >> 16) & 0xff) : 4;
+        const int32_t push_min_rows = ((pub.mode >> 8) & 0xff) ? 16 * ((pub.mode >> 8) & 0xff) : PUSH_MIN_ROWS;
+        cx.scatter = reads_elsewhere && !pub.mc && (chunk_last_row - cp->first_row + 1 > scatter_factor * (n_rec + CVR_W));
         const bool publishing = reads_elsewhere && !cx.scatter; // range pushes behind the watermark
         int32_t pushed_upto = cp->first_row; // kPublish: first row of the chunk not yet sent to the peers
         cx.split1 = cp->split1;
@@ -449,7 +452,7 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
                 f = min(f, __shfl_xor_sync(FULL, f, 1));
                 f = min(f, __shfl_xor_sync(FULL, f, 2));
                 f = min(f, __shfl_xor_sync(FULL, f, 4));
-                if (f - pushed_upto + 1 >= PUSH_MIN_ROWS) {
+                if (f - pushed_upto + 1 >= push_min_rows) {
                     publish_rows(cx, pushed_upto, f, t);
                     pushed_upto = f + 1;
                 }
@@ -612,9 +615,10 @@ __global__ void cvr_peer_barrier_kernel(const __grid_constant__ CvrBarrier b)
 //   41.3, road 342.8 / 354.6 / 370.9 for 7x7 / 9x6 / 11x5 -- short rows want more warps, long regular rows the
 //   larger tile (fewer per-tile flag/carry operations per element);
 //   profiles/r02_kernel_ab_l1_capacity.txt   7x6 against 7x7: R-MAT-24 1316 / 1354, web 38.9 / 40.9, road 357 / 359
-//   -- six blocks need 99 KB of shared memory per SM, which leaves the x gather 156 KB of L1 instead of 124 KB,
-//   and 78 registers per thread instead of 72 with spills.  What the gather needs from L1 is room for the misses
-//   in flight: padding the blocks to 174 KB per SM (L1 60 KB) slows R-MAT-24 from 1390 to 2018 us.
+//   -- 78 registers per thread instead of 72 with spills.  The same file records what the x gather needs from L1:
+//   room for its misses in flight.  The driver configures 132 KB of shared memory (L1 124 KB) for these kernels;
+//   124 KB are enough (156 KB: no change), but 92 / 60 / 28 KB of L1 cost R-MAT-24 15 / 50 / 180 %, which is why
+//   nothing that needs more shared memory per warp (record ring, deeper TMA ring, x cache) ever paid off.
 struct Variant {
     const char* name;
     int tb, nb;
@@ -681,6 +685,12 @@ struct TileOps {
         cudaFuncAttributes a;
         cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, false>);
         cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, true>);
+    }
+    // shared-memory carve-out as a percentage of the SM's 228 KB (-1: the driver's choice)
+    static void set_carveout(int pct)
+    {
+        cudaFuncSetAttribute(cvr_spmv_tile_kernel<TB, NB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(cvr_spmv_tile_kernel<TB, NB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
 };
 
@@ -789,6 +799,10 @@ int cvr_launch_spmv(int variant, const CvrChunk* chunks, int32_t n_chunks, const
     // iteration on) the previous iteration's epilogue: launch as its programmatic dependent
     const bool pdl = pdl_enabled() && !(pub && (publish->mode & 8)); // mode bit 3: two shards share this device
     const bool programmatic = pdl && (after_clear_kernel || (pub && y_is_clear)) && !ev_begin;
+    if (const char* co = getenv("CVR_SMEM_CARVEOUT")) { // experiment: L1 size against shared-memory carve-out
+        const int pct = atoi(co);
+        CVR_FOR_VARIANT(v, P::set_carveout(pct))
+    }
     // the chunk queue pays off when a warp walks many chunks (R-MAT-24, 16 per warp: 1399 -> 1354 us); with one
     // or two chunks per warp the ticket only costs (web 38.9 -> 40.9 us)
     if ((int64_t)(chunk_end - chunk_begin) < 4 * (int64_t)resident * WARPS) chunk_queue = nullptr;

@@ -140,6 +140,9 @@ class PeerPublisher:
                 needs[1:1 + hi - lo] |= (recv[q] << q)
             del used, parts, recv
             needs[1:] &= 0xFF ^ (1 << rank)  # own rows are written in place (y aliases my slice of x)
+            dry = os.environ.get("CVR_PUBLISH_DRY_RANKS", "")  # diagnosis only (results are WRONG): these ranks run the
+            if dry and str(rank) in dry.split(","):            # publishing sweep but send nothing
+                needs.zero_()
             self.needs = needs
             self.chunk_any = torch.zeros(matrix.n_chunks, dtype=torch.uint8, device=needs.device)
             _lib.check(self._lib.cvr_chunk_needs(matrix._h, needs.data_ptr(), self.chunk_any.data_ptr(), 0))
@@ -151,6 +154,8 @@ class PeerPublisher:
             p.n_dst = world
             p.self = rank  # dst[rank] is this GPU's own buffer (y aliases its slice of it, mode bit 2)
             p.mode = int(os.environ.get("CVR_PUBLISH_MODE", "0"))
+            p.mode |= (int(os.environ.get("CVR_PUSH_MIN_ROWS", "0")) // 16 & 0xFF) << 8   # experiment knobs
+            p.mode |= (int(os.environ.get("CVR_SCATTER_FACTOR", "0")) & 0xFF) << 16
             p.row_offset = self.cuts[rank] - 1
             p.needs = self.needs.data_ptr() if self.needs is not None else None
             p.chunk_any = self.chunk_any.data_ptr() if self.needs is not None else None
