@@ -575,39 +575,101 @@ int create_common(const cvr_csr_t* csr, int32_t n_chunks, int device, bool csr_o
 
 } // namespace
 
-cudaError_t cvr_dev_malloc(void** p, size_t bytes, cudaStream_t stream)
+// ---- device memory of the library: cudaMalloc underneath, freed blocks kept for the next matrix.
+// (The CUDA stream-ordered pool was tried first: warm it is as fast, but GROWING it costs 100-190 ms per GB -- road,
+// first matrix of a process: 186 ms against 27 ms with cudaMalloc; R-MAT-24: 60-600 ms against 11 ms --
+// profiles/r02_create_trace.txt.)  Contract: a block is freed only after the work that used it has completed; every
+// call site synchronises its stream (or the device) first, so a cached block can be handed out again at once.
+namespace {
+struct CachedBlock {
+    void* ptr;
+    size_t bytes;
+    int device;
+};
+std::mutex g_mem_mutex;
+std::vector<CachedBlock> g_live;   // blocks handed out (ptr -> size, device)
+std::vector<CachedBlock> g_cached; // freed blocks kept for reuse
+size_t g_cached_bytes = 0;
+size_t g_keep_bytes = (size_t)2 << 30;                 // cap of the cache (CVR_POOL_KEEP_MB)
+constexpr size_t CACHE_MAX_BLOCK = (size_t)768 << 20;  // larger blocks always go back to the driver
+} // namespace
+
+cudaError_t cvr_dev_malloc(void** p, size_t bytes, cudaStream_t)
 {
     if (bytes == 0) bytes = 1;
+    bytes = (bytes + 255) & ~(size_t)255;
+    int dev = 0;
+    cudaGetDevice(&dev);
     if (pool_enabled()) {
-        const cudaError_t e = cudaMallocAsync(p, bytes, stream);
-        if (e == cudaSuccess) return e;
-        cudaGetLastError(); // pools unsupported or exhausted: fall through to cudaMalloc
+        std::lock_guard<std::mutex> lock(g_mem_mutex);
+        size_t best = g_cached.size();
+        for (size_t k = 0; k < g_cached.size(); k++) {
+            const CachedBlock& c = g_cached[k];
+            if (c.device == dev && c.bytes >= bytes && c.bytes <= bytes + bytes / 4 + 4096 &&
+                (best == g_cached.size() || c.bytes < g_cached[best].bytes))
+                best = k;
+        }
+        if (best < g_cached.size()) {
+            const CachedBlock c = g_cached[best];
+            g_cached[best] = g_cached.back();
+            g_cached.pop_back();
+            g_cached_bytes -= c.bytes;
+            g_live.push_back(c);
+            *p = c.ptr;
+            return cudaSuccess;
+        }
     }
-    return cudaMalloc(p, bytes);
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && pool_enabled()) { // out of memory: give the cache back and retry once
+        cudaGetLastError();
+        std::vector<CachedBlock> drop;
+        {
+            std::lock_guard<std::mutex> lock(g_mem_mutex);
+            for (size_t k = 0; k < g_cached.size();)
+                if (g_cached[k].device == dev) {
+                    drop.push_back(g_cached[k]);
+                    g_cached_bytes -= g_cached[k].bytes;
+                    g_cached[k] = g_cached.back();
+                    g_cached.pop_back();
+                } else k++;
+        }
+        for (const CachedBlock& c : drop) cudaFree(c.ptr);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess && pool_enabled()) {
+        std::lock_guard<std::mutex> lock(g_mem_mutex);
+        g_live.push_back(CachedBlock{*p, bytes, dev});
+    }
+    return e;
 }
 
-void cvr_dev_free(void* p, cudaStream_t stream)
+void cvr_dev_free(void* p, cudaStream_t)
 {
     if (!p) return;
-    if (pool_enabled() && cudaFreeAsync(p, stream) == cudaSuccess) return;
-    cudaGetLastError();
-    cudaFree(p); // also correct for memory that came from cudaMallocAsync
+    if (pool_enabled()) {
+        std::lock_guard<std::mutex> lock(g_mem_mutex);
+        for (size_t k = 0; k < g_live.size(); k++)
+            if (g_live[k].ptr == p) {
+                const CachedBlock c = g_live[k];
+                g_live[k] = g_live.back();
+                g_live.pop_back();
+                if (c.bytes <= CACHE_MAX_BLOCK && g_cached_bytes + c.bytes <= g_keep_bytes) {
+                    g_cached.push_back(c);
+                    g_cached_bytes += c.bytes;
+                    return;
+                }
+                break;
+            }
+    }
+    cudaFree(p);
 }
 
-void cvr_pool_setup(int device)
+void cvr_pool_setup(int)
 {
-    if (!pool_enabled()) return;
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) {
-        cudaGetLastError();
-        return;
+    if (const char* e = getenv("CVR_POOL_KEEP_MB")) {
+        std::lock_guard<std::mutex> lock(g_mem_mutex);
+        g_keep_bytes = (size_t)atoll(e) << 20;
     }
-    // freed blocks stay in the pool up to this many bytes (default 0 = everything goes back to the driver at the
-    // next synchronisation, which makes every allocation a fresh mapping again); CVR_POOL_KEEP_MB overrides
-    uint64_t keep = (uint64_t)2 << 30;
-    if (const char* e = getenv("CVR_POOL_KEEP_MB")) keep = (uint64_t)atoll(e) << 20;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    cudaGetLastError();
 }
 
 extern "C" {

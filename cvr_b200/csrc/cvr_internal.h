@@ -128,14 +128,14 @@ int cvr_spmv_resident_warps_per_sm(int variant);
 // its name ("tile7x6", "tile11x5", ...)
 const char* cvr_spmv_kernel_name(int variant);
 
-// Device memory of the library comes from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync):
-// once the pool is warm an allocation is a pool hit -- microseconds, no device-wide synchronisation -- and a free
-// never blocks.  (Measured on B200 with cudaMalloc / cudaFree, profiles/r02_create_trace.txt: the 12 allocations of
-// ONE web-Google-sized matrix took 10-75 ms, a single cudaFree of scratch up to 556 ms; the conversion kernels
-// take 0.26 ms.)  CVR_NO_POOL=1 keeps cudaMalloc / cudaFree.  `stream` orders the allocation / the free.
+// Device memory of the library: cudaMalloc underneath, freed blocks cached for the next matrix (up to 2 GB,
+// CVR_POOL_KEEP_MB; CVR_NO_POOL=1 = plain cudaMalloc / cudaFree).  With cudaMalloc / cudaFree in the creation path the
+// 12 allocations of ONE web-Google-sized matrix took 10-75 ms and a single cudaFree of scratch up to 556 ms, against
+// 0.26 ms of conversion kernels (profiles/r02_create_trace.txt).  A block is freed only after the work that used it
+// has completed (every call site synchronises first); the stream argument is unused and kept for the call sites.
 cudaError_t cvr_dev_malloc(void** p, size_t bytes, cudaStream_t stream);
 void cvr_dev_free(void* p, cudaStream_t stream);
-void cvr_pool_setup(int device); // once per device: keep freed memory cached in the pool (release threshold)
+void cvr_pool_setup(int device); // reads CVR_POOL_KEEP_MB
 
 // force-load the kernels' module so the first timed call does not pay CUDA's lazy loading
 void cvr_preload_convert_kernels();
