@@ -125,7 +125,7 @@ int cvr_launch_column_footprint(const int32_t* cols, int64_t nnz, uint8_t* used,
 int cvr_pick_sweep_variant(int64_t nnz, int64_t n_rows);
 // resident warps per SM of that geometry (sizes the automatic chunk count)
 int cvr_spmv_resident_warps_per_sm(int variant);
-// its name ("tile7x6", "tile11x5", ...)
+// its name ("tile7x5r", "tile11x5", ...)
 const char* cvr_spmv_kernel_name(int variant);
 
 // Device memory of the library: cudaMalloc underneath, freed blocks cached for the next matrix (up to 2 GB,

@@ -5,10 +5,15 @@
 // (paper Alg. 4), including the steal-only chunks (split1 == -1) the
 // reference kernel mishandles.
 //
-// One sweep kernel, cvr_spmv_tile_kernel<TB, NB, kPublish>, in two geometries picked per matrix (see
-// cvr_pick_sweep_variant): TB = 7 steps per walker at 6 resident blocks per SM for short-row matrices,
-// TB = 11 at 5 blocks for long regular rows; <..., kPublish> additionally pushes finished rows to peer
-// GPUs for the iterated multi-GPU SpMV.  What was measured against it on B200 in round 2 and removed
+// One sweep kernel, cvr_spmv_tile_kernel<TB, NB, RD, kPublish>, in two geometries picked per matrix (see
+// cvr_pick_sweep_variant): TB = 7 steps per walker, 5 resident blocks per SM and a 3-deep cp.async record ring
+// for everything but long regular rows, which take TB = 11 at 5 blocks; <..., kPublish> additionally pushes
+// finished rows to peer GPUs for the iterated multi-GPU SpMV.  Two things set the geometry besides the walk
+// itself (profiles/r02_kernel_ab_l1_capacity.txt, r02_kernel_ab_record_ring.txt): the x gather needs L1 for its
+// misses in flight, so the blocks of an SM must fit the 100 KB shared-memory configuration (the kernel asks for
+// it: the driver's own pick is 132 KB), and short-row matrices consume several 32-record batches per tile, which
+// a ring of cp.async copies delivers without a dependent global load in the walk.
+// What was measured against it on B200 in round 2 and removed
 // again (never faster on any BASELINE workload; numbers under profiles/, code in the git history):
 //   * round 1's window kernel (warp-wide segmented reduction) and LDG-streamed walker
 //     (profiles/r02_kernel_ab_round1_generations.jsonl);
@@ -69,6 +74,10 @@ constexpr int32_t PUSH_MIN_ROWS = 64;   // a warp publishes finished rows to the
 #define CVR_TMA_STAGES 1
 #endif
 constexpr int STAGES = CVR_TMA_STAGES; // TMA ring depth per warp (1: the registers are the 2nd buffer)
+// Template parameter RD of the sweep: record batches (32 records, one per lane) are prefetched RD - 1 batches ahead
+// with cp.async (LDGSTS) into a per-warp ring: lane t copies record 32k + t into its own slot and is the only
+// thread that ever reads it, so the ring needs no barrier -- cp.async.wait_group orders a lane's copy before its own
+// shared load.  RD = 0: one batch held in registers, the next one requested when the held one is taken.
 
 template <int TB>
 struct Geo {
@@ -229,7 +238,7 @@ __device__ __forceinline__ void fma_if(double& acc, double a, double x, uint32_t
 __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return ((w * 0x00204081u) >> 21) & 0xfu; }
 
 
-template <int TB, int NB, bool kPublish>
+template <int TB, int NB, int RD, bool kPublish>
 __global__ void __launch_bounds__(WARPS * 32, NB)
 cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, int32_t T,
                      const double* __restrict__ vals, const int32_t* __restrict__ cols,
@@ -241,6 +250,7 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
     __shared__ uint32_t s_flags[WARPS][FLAG_WORDS][32]; // one flag byte per (thread, step)
     __shared__ int32_t s_wb[WARPS][TB][32];             // write-back target per (step, thread)
     __shared__ __align__(8) unsigned long long s_bar[WARPS][STAGES];
+    __shared__ __align__(16) int2 s_rec[WARPS][RD > 0 ? RD : 1][RD > 0 ? 32 : 1]; // record ring (cp.async)
     extern __shared__ __align__(128) unsigned char s_stream[]; // WARPS x STAGES tiles
 
     const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -319,10 +329,32 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
             if (sidx < n_tiles) issue_tile(sidx);
 
         int32_t rb = 0;
-        // the warp holds 32 records (one coalesced 256 B load) and PREFETCHES the next 32: ncu put 25 % of the
-        // sweep's stall samples on the first use of a freshly loaded batch (profiles/r02_final_rmat24_source_top.txt)
-        int2 held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
-        int2 nxt = (32 + t < n_rec) ? rec[32 + t] : make_int2(-1, 0);
+        // batch k = records [32k, 32k + 32): requested RD - 1 batches before it is taken (ncu on road: 46 % of the
+        // sweep's stall samples sat on the first use of a batch requested ONE batch earlier, 3.8 batches per tile).
+        // Exactly one cp.async group is committed per batch index, empty or not, so "batch k has landed" is always
+        // "at most RD - 1 groups pending".
+        const uint32_t my_slot = smem_u32(&s_rec[w][0][RD > 0 ? t : 0]);
+        auto fetch_batch = [&](int32_t k) {
+            const int32_t i = 32 * k + t;
+            if (i < n_rec)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(my_slot + (uint32_t)(k % (RD > 0 ? RD : 1)) * 256u),
+                             "l"(rec + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto take_batch = [&](int32_t k) -> int2 {
+            asm volatile("cp.async.wait_group %0;" ::"n"(RD > 0 ? RD - 1 : 0) : "memory");
+            return (32 * k + t < n_rec) ? s_rec[w][k % (RD > 0 ? RD : 1)][RD > 0 ? t : 0] : make_int2(-1, 0);
+        };
+        int2 held, nxt = make_int2(-1, 0);
+        if constexpr (RD > 0) {
+#pragma unroll
+            for (int k = 0; k < RD; k++) fetch_batch(k);
+            held = take_batch(0);
+        } else {
+            // the warp holds 32 records (one coalesced 256 B load) and requests the next 32 when it takes them
+            held = (t < n_rec) ? rec[t] : make_int2(-1, 0);
+            nxt = (32 + t < n_rec) ? rec[32 + t] : make_int2(-1, 0);
+        }
         double lane_carry = 0.0; // open partial sum of SIMD lane l at the tile boundary
         double carry_slot = 0.0; // private share of t_rets[l] (spmv.cpp:1124)
         // When launched as a programmatic dependent of cvr_clear_rows_kernel everything above (ring
@@ -381,8 +413,13 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
                 // as soon as ANY lane holds a position beyond it -- a vote, not a shuffle through the LSU queue
                 if (__any_sync(FULL, (uint32_t)held.x >= (uint32_t)(ts + TILE))) break;
                 rb += 32;
-                held = nxt;
-                nxt = (rb + 32 + t < n_rec) ? rec[rb + 32 + t] : make_int2(-1, 0);
+                if constexpr (RD > 0) {
+                    fetch_batch(rb / 32 + RD - 1); // into the slot of the batch just used up (my own element of it)
+                    held = take_batch(rb / 32);
+                } else {
+                    held = nxt;
+                    nxt = (rb + 32 + t < n_rec) ? rec[rb + 32 + t] : make_int2(-1, 0);
+                }
             }
             if (t == 0 && split0 != 0) {
                 const uint32_t rel = (uint32_t)(split0 - ts);
@@ -475,6 +512,7 @@ cvr_spmv_tile_kernel(const CvrChunk* __restrict__ chunks, int32_t chunk_begin, i
         }
         if (kPublish && publishing && pushed_upto <= chunk_last_row)
             publish_rows(cx, pushed_upto, chunk_last_row, t); // what the watermark had not reached
+        if constexpr (RD > 0) asm volatile("cp.async.wait_group 0;" ::: "memory"); // the next chunk counts from zero
         chunk = queue ? __shfl_sync(FULL, next_chunk, 0) : next_chunk;
     }
     // the last warp to leave resets the queue for the next launch (every warp has drawn its last ticket by then)
@@ -621,18 +659,28 @@ __global__ void cvr_peer_barrier_kernel(const __grid_constant__ CvrBarrier b)
 //   nothing that needs more shared memory per warp (record ring, deeper TMA ring, x cache) ever paid off.
 struct Variant {
     const char* name;
-    int tb, nb;
+    int tb, nb, rd;
 };
+// The record ring costs shared memory (RD x 1 KB per block) and the x gather wants L1 (above): five blocks with a
+// three-deep ring fit the 100 KB shared-memory configuration (L1 156 KB), six blocks with any ring need the 132 KB one.
+// Same box, kernel us (profiles/r02_kernel_ab_record_ring.txt):
+//                          R-MAT-24    web    road    FEM      records: batches of 32 per 224-element tile
+//   tile7x5r (RD 3, L1 156)  1205.9    36.2   321.7   65.3     R-MAT-24 0.2, web 1.2, road 2.9, FEM 0.3
+//   tile7x6r (RD 4, L1 124)  1278.6    36.7   319.4   66.8
+//   tile7x6  (RD 0, L1 156)  1220.0    38.4   356.5   69.3
+//   tile11x5 (RD 0, L1 124)  1332.7    40.7   370.1   63.2
+// (tile7x6 with the driver's own 132 KB configuration, the round-2 kernel until then: 1312 / 38.6 / 357 / -.)
 constexpr Variant VARIANTS[] = {
-    {"tile7x6", 7, 6},
-    {"tile11x5", 11, 5},
-    {"tile7x7", 7, 7},
+    {"tile7x5r", 7, 5, 3},
+    {"tile11x5", 11, 5, 0},
+    {"tile7x6", 7, 6, 0},
+    {"tile7x6r", 7, 6, 4},
 };
 constexpr int N_VARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
 
 int forced_variant()
 {
-    // CVR_SPMV_KERNEL = tile7x6 | tile11x5 | tile7x7 overrides the per-matrix choice; read per call so
+    // CVR_SPMV_KERNEL = tile7x5r | tile11x5 | tile7x6 | tile7x6r overrides the per-matrix choice; read per call so
     // that tools/kernel_ab.py and the parity suite can switch it at run time
     const char* e = getenv("CVR_SPMV_KERNEL");
     if (!e || !*e) return -1;
@@ -659,12 +707,12 @@ cudaError_t launch_ex(K kernel, int blocks, int threads, int smem, cudaStream_t 
 }
 
 // one entry per geometry: occupancy query and launch, plain and publishing flavour
-template <int TB, int NB>
+template <int TB, int NB, int RD>
 struct TileOps {
     static int resident_blocks()
     {
         int blocks = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<TB, NB, false>, WARPS * 32,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvr_spmv_tile_kernel<TB, NB, RD, false>, WARPS * 32,
                                                           Geo<TB>::DYN_SMEM) != cudaSuccess)
             return 0;
         return blocks;
@@ -675,30 +723,37 @@ struct TileOps {
                               const CvrPublish& pub, unsigned int* queue)
     {
         if (publish)
-            return launch_ex(cvr_spmv_tile_kernel<TB, NB, true>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
+            return launch_ex(cvr_spmv_tile_kernel<TB, NB, RD, true>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
                              programmatic, chunks, chunk_begin, chunk_end, vals, cols, record, x, y, pub, queue);
-        return launch_ex(cvr_spmv_tile_kernel<TB, NB, false>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
+        return launch_ex(cvr_spmv_tile_kernel<TB, NB, RD, false>, blocks, WARPS * 32, Geo<TB>::DYN_SMEM, stream,
                          programmatic, chunks, chunk_begin, chunk_end, vals, cols, record, x, y, pub, queue);
-    }
-    static void preload()
-    {
-        cudaFuncAttributes a;
-        cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, false>);
-        cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, true>);
     }
     // shared-memory carve-out as a percentage of the SM's 228 KB (-1: the driver's choice)
     static void set_carveout(int pct)
     {
-        cudaFuncSetAttribute(cvr_spmv_tile_kernel<TB, NB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(cvr_spmv_tile_kernel<TB, NB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(cvr_spmv_tile_kernel<TB, NB, RD, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(cvr_spmv_tile_kernel<TB, NB, RD, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    static void preload()
+    {
+        cudaFuncAttributes a;
+        cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, RD, true>);
+        cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, RD, false>);
+        // ask for the shared-memory configuration the NB resident blocks need and no more: the driver's own choice is
+        // sized for the blocks shared memory ALONE would admit, and every step up (132 -> 164 -> 196 KB) takes L1 away
+        // from the x gather (profiles/r02_kernel_ab_l1_capacity.txt)
+        const size_t need = (size_t)NB * (a.sharedSizeBytes + Geo<TB>::DYN_SMEM + 1024);
+        int pct = (int)((need * 100 + 233471) / 233472);
+        set_carveout(pct > 100 ? 100 : pct);
     }
 };
 
-#define CVR_FOR_VARIANT(v, expr)                         \
-    switch (v) {                                         \
-    case 0: { using P = TileOps<7, 6>; expr; } break;    \
-    case 1: { using P = TileOps<11, 5>; expr; } break;   \
-    default: { using P = TileOps<7, 7>; expr; } break;   \
+#define CVR_FOR_VARIANT(v, expr)                            \
+    switch (v) {                                            \
+    case 0: { using P = TileOps<7, 5, 3>; expr; } break;    \
+    case 1: { using P = TileOps<11, 5, 0>; expr; } break;   \
+    case 2: { using P = TileOps<7, 6, 0>; expr; } break;    \
+    default: { using P = TileOps<7, 6, 4>; expr; } break;   \
     }
 
 // resident blocks per SM of a variant on the current device (cached per device and variant)
@@ -735,9 +790,9 @@ bool pdl_enabled()
 
 } // namespace
 
-// Geometry for a matrix with `nnz` stored elements in `n_rows` rows: the larger tile pays off when rows
-// are long and regular (few row switches per tile: FEM), more resident warps when they are short or
-// skewed (web, road, R-MAT).  CVR_SPMV_KERNEL overrides.
+// Geometry for a matrix with `nnz` stored elements in `n_rows` rows: the large tile pays off when rows are long and
+// regular (few row switches per tile: FEM); everything else takes the small tile with the record ring.
+// CVR_SPMV_KERNEL overrides.
 int cvr_pick_sweep_variant(int64_t nnz, int64_t n_rows)
 {
     const int f = forced_variant();

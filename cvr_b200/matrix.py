@@ -123,7 +123,7 @@ class CvrMatrix:
 
     @property
     def kernel_name(self) -> str:
-        """The sweep geometry picked for this matrix ("tile7x6", "tile11x5"; CVR_SPMV_KERNEL overrides)."""
+        """The sweep geometry picked for this matrix ("tile7x5r", "tile11x5"; CVR_SPMV_KERNEL overrides)."""
         return self._lib.cvr_kernel_variant(self._h).decode()
 
     def column_footprint(self, used_dev, stream: int = 0) -> None:

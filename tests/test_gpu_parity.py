@@ -29,7 +29,7 @@ def cvr(native_lib):
 
 # every test of this module runs once per sweep geometry: the per-matrix choice (cvr_pick_sweep_variant)
 # and each geometry forced through CVR_SPMV_KERNEL (read per launch)
-@pytest.fixture(autouse=True, params=["auto", "tile7x6", "tile11x5", "tile7x7"])
+@pytest.fixture(autouse=True, params=["auto", "tile7x5r", "tile11x5", "tile7x6", "tile7x6r"])
 def sweep_geometry(request, monkeypatch):
     if request.param == "auto":
         monkeypatch.delenv("CVR_SPMV_KERNEL", raising=False)

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="rmat24,web,road,fem")
-    ap.add_argument("--variants", default="tile7x6,tile11x5,tile7x7")
+    ap.add_argument("--variants", default="tile7x5r,tile11x5,tile7x6,tile7x6r")
     ap.add_argument("--env", default="CVR_SPMV_KERNEL")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--chunks", type=int, default=0)
