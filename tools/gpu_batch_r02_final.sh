@@ -3,10 +3,9 @@
 # reference arm, ncu launch list of the bench command, one `ncu --set full` capture of the sweep per workload,
 # the conversion kernels' launch list, the CLI side by side with the reference, compute-sanitizer on two parity cases.
 set -x
-O=gpurun_out/r02f
+O=gpurun_out/r02h
 mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
-for w in web rmat24 road; do python tools/kernel_ab.py --workloads $w --env CVR_CHUNK_NNZ --variants 1024,2048,4096,8192 --out $O/ab_chunk_nnz.jsonl 2>/dev/null | grep '^{' | cut -c1-200; done
 python bench.py > $O/bench_default.json 2> $O/bench_default.err; tail -c 400 $O/bench_default.json
 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err; tail -c 300 $O/bench_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench_default.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-cusparse > $O/bench_under_ncu.log 2>&1
