@@ -742,9 +742,15 @@ struct TileOps {
         // ask for the shared-memory configuration the NB resident blocks need and no more: the driver's own choice is
         // sized for the blocks shared memory ALONE would admit, and every step up (132 -> 164 -> 196 KB) takes L1 away
         // from the x gather (profiles/r02_kernel_ab_l1_capacity.txt)
+        set_carveout(carveout_pct());
+    }
+    static int carveout_pct()
+    {
+        cudaFuncAttributes a;
+        if (cudaFuncGetAttributes(&a, cvr_spmv_tile_kernel<TB, NB, RD, false>) != cudaSuccess) return -1;
         const size_t need = (size_t)NB * (a.sharedSizeBytes + Geo<TB>::DYN_SMEM + 1024);
-        int pct = (int)((need * 100 + 233471) / 233472);
-        set_carveout(pct > 100 ? 100 : pct);
+        const int pct = (int)((need * 100 + 233471) / 233472);
+        return pct > 100 ? 100 : pct;
     }
 };
 
