@@ -106,7 +106,8 @@ struct cvr_sharded {
     ncclComm_t comms[CVR_MAX_PEERS] = {};
     bool comms_ready = false;
 
-    ~cvr_sharded()
+    // frees everything the parts hold (the handle can then be rebuilt with other cut points)
+    void release()
     {
         for (int g = 0; g < n; g++) {
             Part& p = parts[g];
@@ -116,6 +117,7 @@ struct cvr_sharded {
         if (comms_ready)
             for (int g = 0; g < n; g++)
                 if (comms[g]) nccl.CommDestroy(comms[g]);
+        comms_ready = false;
         for (int g = 0; g < n; g++) {
             Part& p = parts[g];
             cudaSetDevice(p.device);
@@ -128,8 +130,12 @@ struct cvr_sharded {
             if (p.ev1) cudaEventDestroy(p.ev1);
             if (p.stream) cudaStreamDestroy(p.stream);
             if (p.h) cvr_destroy(p.h);
+            p = Part();
+            comms[g] = nullptr;
         }
+        epoch = 0;
     }
+    ~cvr_sharded() { release(); }
 };
 
 namespace {
@@ -172,6 +178,41 @@ std::vector<int64_t> partition_rows_by_nnz(const cvr_csr_t* csr, int parts, int6
         cuts[(size_t)g] = std::min(std::max(lo, cuts[(size_t)g - 1]), csr->n_rows + 1);
     }
     return cuts;
+}
+
+// New cut points from MEASURED per-part sweep seconds (the C++ twin of cvr_b200/shard.py::rebalance_cuts): every row is
+// charged its model weight (nnz, + row_weight if not empty) scaled by (seconds of its part / model weight of its part),
+// and the rows are re-cut into parts of equal charged cost.
+std::vector<int64_t> rebalance_cuts(const cvr_csr_t* csr, const std::vector<int64_t>& cuts, const double* seconds,
+                                    double row_weight)
+{
+    const int parts = (int)cuts.size() - 1;
+    auto weight = [&](int64_t r) { // row r, 1-based
+        const int64_t n = delim_at(csr, r + 1) - delim_at(csr, r);
+        return (double)n + (n > 0 ? row_weight : 0.0);
+    };
+    std::vector<double> scale((size_t)parts, 0.0);
+    double total = 0.0;
+    for (int g = 0; g < parts; g++) {
+        double w = 0.0;
+        for (int64_t r = cuts[(size_t)g]; r < cuts[(size_t)g + 1]; r++) w += weight(r);
+        scale[(size_t)g] = w > 0.0 ? seconds[g] / w : 0.0;
+        total += w > 0.0 ? seconds[g] : 0.0;
+    }
+    std::vector<int64_t> out((size_t)parts + 1);
+    out[0] = 1;
+    out[(size_t)parts] = csr->n_rows + 1;
+    double cum = 0.0;
+    int next = 1, g = 0;
+    for (int64_t r = 1; r <= csr->n_rows && next < parts; r++) {
+        while (g + 1 < parts && r >= cuts[(size_t)g + 1]) g++;
+        cum += weight(r) * scale[(size_t)g];
+        // rows 1..r reach the target of cut `next`: the part starts at the row after
+        while (next < parts && cum >= total * next / parts) out[(size_t)next++] = std::min(r + 1, csr->n_rows + 1);
+    }
+    for (; next < parts; next++) out[(size_t)next] = csr->n_rows + 1;
+    for (int k = 1; k <= parts; k++) out[(size_t)k] = std::max(out[(size_t)k], out[(size_t)k - 1]);
+    return out;
 }
 
 // Rows [lo, hi) of the host CSR as a CSR of its own: local rows 1..n, global columns, delimiters re-based,
@@ -332,9 +373,96 @@ int sync_all(cvr_sharded* s)
     return CVR_OK;
 }
 
+// Builds the parts of `s` for the cut points in s->cuts: shard CSRs, CVR conversion on every device, x buffers,
+// flags, peer access, footprints.
+int build_parts(cvr_sharded* s, const cvr_csr_t* view_ptr, const cvr_csr_t* csr, int32_t n_chunks_per_device,
+                const int* devices, int n_devices, int flags)
+{
+    int rc = CVR_OK;
+    for (int g = 0; g < n_devices && rc == CVR_OK; g++) {
+        Part& p = s->parts[g];
+        p.device = devices[g];
+        p.lo = s->cuts[(size_t)g];
+        p.hi = s->cuts[(size_t)g + 1];
+        HostShard hs;
+        build_shard(view_ptr, p.lo, p.hi, csr->nnz, &hs);
+        p.n_local = hs.n_local;
+        cvr_csr_t sub{};
+        sub.n_rows = hs.n_local;
+        sub.n_cols = csr->n_cols;
+        sub.nnz = (int64_t)hs.val.size();
+        sub.val = hs.val.data();
+        sub.col = hs.col.data();
+        sub.row_delim64 = hs.rd.data();
+        std::vector<int32_t> rd32;
+        if (sub.nnz <= 0x7fffffffLL) { // the 32-bit entry where it fits, like the single-GPU path
+            rd32.assign(hs.rd.begin(), hs.rd.end());
+            sub.row_delim32 = rd32.data();
+            sub.row_delim64 = nullptr;
+        }
+        rc = cvr_create(&sub, n_chunks_per_device, p.device, &p.h);
+        if (rc != CVR_OK) break;
+        cudaError_t e = cudaSetDevice(p.device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&p.ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&p.ev1);
+        const size_t xbytes = sizeof(double) * (size_t)(std::max(csr->n_cols, csr->n_rows) + 1);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p.X[0]), xbytes);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p.X[1]), xbytes);
+        if (e == cudaSuccess) e = cudaMemset(p.X[0], 0, xbytes);
+        if (e == cudaSuccess) e = cudaMemset(p.X[1], 0, xbytes);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p.flags), sizeof(uint32_t) * 64);
+        if (e == cudaSuccess) e = cudaMemset(p.flags, 0, sizeof(uint32_t) * 64);
+        if (e != cudaSuccess) rc = fail(CVR_ERR_CUDA, "device %d set-up failed: %s", p.device, cudaGetErrorString(e));
+    }
+    // every device may store into every other device's x buffers and flag array
+    if (rc == CVR_OK && n_devices > 1) {
+        for (int a = 0; a < n_devices && rc == CVR_OK; a++)
+            for (int b = 0; b < n_devices && rc == CVR_OK; b++) {
+                const int da = devices[a], db = devices[b];
+                if (da == db) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, da, db);
+                if (!can) {
+                    if (!(flags & CVR_SHARD_NCCL))
+                        rc = fail(CVR_ERR_CUDA, "device %d cannot access device %d: use CVR_SHARD_NCCL", da, db);
+                    continue;
+                }
+                cudaSetDevice(da);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    rc = fail(CVR_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", da, db, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+    }
+    if (rc == CVR_OK && n_devices > 1 && !(flags & CVR_SHARD_NCCL) && !(flags & CVR_SHARD_DENSE) &&
+        csr->n_rows == csr->n_cols)
+        rc = build_needs(s);
+    return rc;
+}
+
 } // namespace
 
 extern "C" {
+
+static // Seconds of the sweep kernel of every part inside the real iteration (x <- A x, publishing included): a few warm-up
+// iterations, then timed ones with per-launch events on every part's handle.
+int measure_parts(cvr_sharded* s, double* seconds)
+{
+    std::vector<double> x((size_t)s->n_cols + 1, 1.0), y((size_t)s->n_rows + 1, 0.0);
+    x[0] = 0.0;
+    int rc = cvr_sharded_spmv(s, x.data(), y.data(), 3, 1, nullptr);
+    for (int g = 0; g < s->n && rc == CVR_OK; g++) rc = cvr_set_kernel_timing(s->parts[g].h, 1);
+    if (rc == CVR_OK) rc = cvr_sharded_spmv(s, x.data(), y.data(), 6, 1, nullptr);
+    for (int g = 0; g < s->n; g++) {
+        double total = 0.0;
+        int64_t launches = 0;
+        if (rc == CVR_OK) rc = cvr_get_kernel_timing(s->parts[g].h, &total, &launches);
+        seconds[g] = launches > 0 ? total / (double)launches : 0.0;
+        cvr_set_kernel_timing(s->parts[g].h, 0);
+    }
+    return rc;
+}
 
 int cvr_create_sharded(const cvr_csr_t* csr, int32_t n_chunks_per_device, const int* devices, int n_devices,
                        int flags, cvr_sharded_t** out)
@@ -388,66 +516,28 @@ int cvr_create_sharded(const cvr_csr_t* csr, int32_t n_chunks_per_device, const 
     if (const char* e = getenv("CVR_SHARD_ROW_WEIGHT")) row_weight = atof(e);
     s->cuts = partition_rows_by_nnz(&view, n_devices, csr->nnz, row_weight);
 
-    int rc = CVR_OK;
-    for (int g = 0; g < n_devices && rc == CVR_OK; g++) {
-        Part& p = s->parts[g];
-        p.device = devices[g];
-        p.lo = s->cuts[(size_t)g];
-        p.hi = s->cuts[(size_t)g + 1];
-        HostShard hs;
-        build_shard(&view, p.lo, p.hi, csr->nnz, &hs);
-        p.n_local = hs.n_local;
-        cvr_csr_t sub{};
-        sub.n_rows = hs.n_local;
-        sub.n_cols = csr->n_cols;
-        sub.nnz = (int64_t)hs.val.size();
-        sub.val = hs.val.data();
-        sub.col = hs.col.data();
-        sub.row_delim64 = hs.rd.data();
-        std::vector<int32_t> rd32;
-        if (sub.nnz <= 0x7fffffffLL) { // the 32-bit entry where it fits, like the single-GPU path
-            rd32.assign(hs.rd.begin(), hs.rd.end());
-            sub.row_delim32 = rd32.data();
-            sub.row_delim64 = nullptr;
-        }
-        rc = cvr_create(&sub, n_chunks_per_device, p.device, &p.h);
-        if (rc != CVR_OK) break;
-        cudaError_t e = cudaSetDevice(p.device);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreate(&p.ev0);
-        if (e == cudaSuccess) e = cudaEventCreate(&p.ev1);
-        const size_t xbytes = sizeof(double) * (size_t)(std::max(csr->n_cols, csr->n_rows) + 1);
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p.X[0]), xbytes);
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p.X[1]), xbytes);
-        if (e == cudaSuccess) e = cudaMemset(p.X[0], 0, xbytes);
-        if (e == cudaSuccess) e = cudaMemset(p.X[1], 0, xbytes);
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p.flags), sizeof(uint32_t) * 64);
-        if (e == cudaSuccess) e = cudaMemset(p.flags, 0, sizeof(uint32_t) * 64);
-        if (e != cudaSuccess) rc = fail(CVR_ERR_CUDA, "device %d set-up failed: %s", p.device, cudaGetErrorString(e));
-    }
-    // every device may store into every other device's x buffers and flag array
-    if (rc == CVR_OK && n_devices > 1) {
-        for (int a = 0; a < n_devices && rc == CVR_OK; a++)
-            for (int b = 0; b < n_devices && rc == CVR_OK; b++) {
-                const int da = devices[a], db = devices[b];
-                if (da == db) continue;
-                int can = 0;
-                cudaDeviceCanAccessPeer(&can, da, db);
-                if (!can) {
-                    if (!(flags & CVR_SHARD_NCCL))
-                        rc = fail(CVR_ERR_CUDA, "device %d cannot access device %d: use CVR_SHARD_NCCL", da, db);
-                    continue;
-                }
-                cudaSetDevice(da);
-                const cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
-                    rc = fail(CVR_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", da, db, cudaGetErrorString(e));
-                cudaGetLastError();
+    int rc = build_parts(s, &view, csr, n_chunks_per_device, devices, n_devices, flags);
+    // CVR_SHARD_REBALANCE = R: up to R rounds of re-cutting the shards from the MEASURED sweep time of every part
+    // (iterated SpMV only, i.e. square matrices; cvr_b200/dist.py does the same for the one-process-per-GPU host)
+    int rounds = 0;
+    if (const char* e = getenv("CVR_SHARD_REBALANCE")) rounds = atoi(e);
+    if (n_devices > 1 && csr->n_rows == csr->n_cols)
+        for (int r = 0; r < rounds && rc == CVR_OK; r++) {
+            double seconds[CVR_MAX_PEERS] = {};
+            rc = measure_parts(s, seconds);
+            if (rc != CVR_OK) break;
+            double worst = 0.0, mean = 0.0;
+            for (int g = 0; g < n_devices; g++) {
+                worst = std::max(worst, seconds[g]);
+                mean += seconds[g] / n_devices;
             }
-    }
-    if (rc == CVR_OK && n_devices > 1 && !(flags & CVR_SHARD_NCCL) && !(flags & CVR_SHARD_DENSE) &&
-        csr->n_rows == csr->n_cols)
-        rc = build_needs(s);
+            if (worst <= 1.03 * mean) break;
+            const std::vector<int64_t> cuts = rebalance_cuts(&view, s->cuts, seconds, row_weight);
+            if (cuts == s->cuts) break;
+            s->release();
+            s->cuts = cuts;
+            rc = build_parts(s, &view, csr, n_chunks_per_device, devices, n_devices, flags);
+        }
     if (rc != CVR_OK) {
         delete s;
         return rc;

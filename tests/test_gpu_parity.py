@@ -400,3 +400,26 @@ def test_tiny_random_matrices_property(cvr):
             assert_structure_equal(m.export(), want, f"case {case} lens={lens} T={T}")
             y, _ = m.spmv(x)
             assert_y_close(y, csr, x, f"case {case} lens={lens} T={T}")
+
+
+def test_chunk_queue_with_many_small_chunks(cvr, monkeypatch):
+    """The sweep hands out chunks beyond a warp's first from an atomic ticket queue once a launch covers at least four
+    chunks per resident warp (cvr_launch_spmv); the queue resets itself when the last warp leaves.  A matrix cut into
+    16 000 chunks of ~20 elements crosses that threshold on a B200 (<= 3552 resident warps): y must be right on
+    every one of several back-to-back launches, with the queue and with the static round robin, and the two must
+    agree to rounding (only the order of the atomic additions into rows shared by chunks may differ)."""
+    from cvr_b200 import gen
+    d = gen.random_sparse(60000, 50000, 320000, seed=48, empty_frac=0.2, long_rows=3, long_len=9000)
+    csr = to_oracle_csr(d)
+    T = min(16000, csr.nnz // 16)
+    x = np.random.default_rng(11).uniform(-1, 1, csr.n_cols + 1)
+    ys = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CVR_DYNAMIC_CHUNKS", mode)
+        with cvr.CvrMatrix(d.to_host(), T) as m:
+            for rep in range(4):  # the queue counters must come back to zero after every launch
+                y, _ = m.spmv(x, iters=1 if rep < 3 else 5)
+                assert_y_close(y, csr, x, f"queue={mode} launch {rep}")
+            ys[mode] = y
+    assert_y_close(ys["1"], csr, x, "queue on, final")
+    assert np.max(np.abs(ys["1"] - ys["0"])) <= 1e-12 * np.max(np.abs(ys["0"]))

@@ -115,3 +115,32 @@ def test_sharded_accepts_the_reference_last_delimiter_and_rejects_garbage(cvr):
             s.spmv(np.ones(701), iters=2, feed_y_to_x=True)
         y, _ = s.spmv(np.ones(701))
         step_check(to_oracle_csr(rect), np.ones(701), y, "rectangular sharded")
+
+
+@pytest.mark.parametrize("devices", device_lists(), ids=lambda d: "dev" + "".join(map(str, d)))
+def test_sharded_rebalance_from_measured_sweep_times(cvr, devices, monkeypatch):
+    """CVR_SHARD_REBALANCE: cvr_create_sharded times every part's sweep inside the real iteration and re-cuts the rows
+    (the C++ twin of shard.rebalance_cuts).  Whatever the measured times are -- shards sharing one GPU time each other's
+    kernels -- the result must be a valid partition (monotone cuts over all rows, every row owned once), every shard
+    must convert to what the reference gives on its sub-CSR, and the iterated SpMV must stay right step by step."""
+    from cvr_b200 import gen, shard
+    monkeypatch.setenv("CVR_SHARD_REBALANCE", "2")
+    d = gen.rmat(13, 16, seed=86, row_normalise=True)
+    h = d.to_host()
+    csr = to_oracle_csr(h)
+    x0 = np.random.default_rng(8).uniform(-1, 1, csr.n_cols + 1)
+    x0[0] = 0.0
+    with cvr.ShardedCvr(h, devices, n_chunks=29) as s:
+        info = s.info
+        lo, hi = info["row_begin"], info["row_end"]
+        assert lo[0] == 1 and hi[-1] == h.n_rows + 1 and all(a <= b for a, b in zip(lo, hi))
+        assert all(hi[g] == lo[g + 1] for g in range(len(devices) - 1))
+        for g in range(len(devices)):
+            sub = shard.shard_csr(h, lo[g], hi[g])
+            want = oracle.convert(to_oracle_csr(sub), 29, "port", fill_missing_tail=True)
+            assert_structure_equal(s.part_export(g), want, f"re-cut shard {g} of {devices}")
+        prev = x0
+        for k in range(1, 4):
+            xk, _ = s.spmv(x0, iters=k, feed_y_to_x=True)
+            step_check(csr, prev, xk, f"re-cut {devices} iteration {k}")
+            prev = xk
