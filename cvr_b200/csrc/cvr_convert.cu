@@ -4,17 +4,24 @@
 // every 8-element step of a chunk on one OpenMP thread, refilling empty SIMD lanes
 // (feeding, :821-868) or splitting the longest lane (stealing, :869-943) and gathers
 // 8 values + 8 columns per step (:963-977).  Here the same greedy schedule is split
-// into two kernels:
+// into kernels:
 //
-//   cvr_schedule_warp_kernel  one WARP per chunk.  Event-driven restatement of the lane
-//                        scheduler: instead of visiting every step it jumps from one
-//                        "a lane ran empty" event to the next (min over the 8 lane
-//                        counters).  Emits the reference's record / split / tail /
-//                        nnz_rows metadata bit-exactly, plus a scratch list of
-//                        (position, source offset) segment starts.  Integer only.
+//   cvr_row_bitmap_kernel       one bit per row: "not empty" (n_rows / 8 bytes, one streaming pass).
+//   cvr_schedule_group_kernel   the default scheduler: EIGHT THREADS per chunk (thread l is SIMD lane l; a warp
+//                        advances four chunks per instruction stream, chunks are fetched dynamically per
+//                        group).  Event-driven restatement of the lane scheduler: instead of visiting every
+//                        step it jumps from one "a lane ran empty" event to the next (min over the 8 lane
+//                        counters); "the next k non-empty rows" come from the bitmap (funnel-shifted window +
+//                        select-n-th-set-bit).  Emits the reference's record / split / tail / nnz_rows
+//                        metadata bit-exactly, plus a scratch list of (position, source offset) segment
+//                        starts.  Integer only.
+//   cvr_schedule_warp_kernel    round 1's scheduler, one WARP per chunk over the delimiter array
+//                        (CVR_SCHEDULE=warp; kept parity-tested: test_warp_per_chunk_scheduler_still_bit_exact).
 //   cvr_permute_kernel   one WARP per chunk.  Bandwidth-bound: expands the segment list
 //                        into a source index per CVR element (32 elements = 4 steps x 8
 //                        lanes per warp pass, coalesced stores) and moves vals/cols.
+//   cvr_mark_boundary_kernel / cvr_collect_rows_kernel   the lists of accumulated and never-written rows the
+//                        sweep clears (cvr_build_row_lists).
 //
 // Layout written: vals[nnz] f64 and cols[nnz] i32 with element (step i, lane l) of a
 // chunk at start + 8*i + l -- the reference's layout (SURVEY.md 8a-R2 note (ii)).
