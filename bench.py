@@ -2,7 +2,8 @@
 """bench.py -- CVR SpMV throughput on B200 (GFLOP/s = 2*nnz/t, achieved HBM GB/s, roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rmat24|web|fem|road|rmat:S|rmat28]
-                    [--impl ours|reference] [--chunks T] [--no-subs]
+                    [--impl ours|reference] [--chunks T] [--no-subs] [--rebalance R] [--multicast on|off]
+                    [--exchange peer|nccl] [--row-weight W] [--dense-exchange]
 
 A "step" is one SpMV pass of the converted matrix: clear the accumulated rows of y + the sweep
 kernel (for N > 1 followed by the y -> x exchange of the iterated SpMV).  The conversion (CSR -> CVR
@@ -14,7 +15,11 @@ the largest configuration that fits one GPU, and one of the two the north star s
 At N = 1 the other single-GPU configs (web-Google-shaped, FEM 100^3, road 24M) are measured in the
 same run and reported as sub-records under "workloads" (value, ms_per_step, roofline.frac, traffic,
 parity each).  At N > 1 the SAME R-MAT-24 matrix is row-sharded by nnz over the ranks (strong
-scaling) and every step ends with the exchange that rebuilds the replicated x from the y shards.
+scaling) and every step ends with the exchange that rebuilds the replicated x from the y shards
+(--exchange peer: fused into the sweep over peer memory, optionally through an NVSwitch multicast
+address with --multicast on; --exchange nccl: all-gather).  Before the timed region the shards are
+re-cut from the MEASURED sweep time of every rank (--rebalance R rounds, 0 = keep the nnz cut);
+`--workload rmat28` is BASELINE configs[4], generated per row shard.
 
 Parity is checked INSIDE the bench: the y of the timed configuration is compared row by row with a
 device CSR product (cvr_verify_csr, |dy| <= 1e-12 * sum|a x|), and for N > 1 three iterations of the
